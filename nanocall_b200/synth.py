@@ -1,0 +1,81 @@
+"""Synthetic R7.3-style event tables, used by tests, bench.py and the
+golden-vector generator.  Pure numpy, deterministic for a given seed.
+
+Per read: a uniform random base stream; event i sits on the 6-mer starting at base pos_i, where
+pos advances by 0 / 1 / 2 bases with probability p_stay / 1-p_stay-p_skip / p_skip -- the
+stay/step/skip walk behind nanocall's transition model (State_Transitions.hpp:125-144,
+CLI defaults --pr-stay .1 --pr-skip .3, nanocall.cpp:84-85).  Per event:
+mean ~ N(scale*mu_s + shift + drift*t, (var*sigma_s)^2), stdv ~ InvGauss(scale_sd*eta_s,
+var_sd*lambda_s) with lambda = eta^3 / sd_stdv^2 (Pore_Model.hpp:112), clamped to (0, 4]
+(the reader's filter, Fast5_Summary.hpp:734-745), length ~ max(0.002, Exp(0.02 s)),
+start = running sum of lengths in seconds from strand start.
+"""
+import numpy as np
+
+N_STATES = 4096
+IDENTITY_PARAMS = (1.0, 0.0, 0.0, 1.0, 1.0, 1.0)  # scale, shift, drift, var, scale_sd, var_sd
+
+
+def kmer_walk(rng, n_events, p_stay=0.1, p_skip=0.3):
+    """State index per event for one read (A=0,C=1,G=2,T=3, first base in the high bits)."""
+    u = rng.random(n_events)
+    move = np.where(u < p_stay, 0, np.where(u < 1.0 - p_skip, 1, 2)).astype(np.int64)
+    move[0] = 0
+    pos = np.cumsum(move)
+    bases = rng.integers(0, 4, size=int(pos[-1]) + 6, dtype=np.int64)
+    kmer = np.zeros(bases.size - 5, dtype=np.int64)
+    for k in range(6):
+        kmer = (kmer << 2) | bases[k:k + kmer.size]
+    return kmer[pos].astype(np.uint16)
+
+
+def make_read(rng, table, n_events, params=IDENTITY_PARAMS, p_stay=0.1, p_skip=0.3):
+    """-> dict(mean, stdv, start: float32[n_events], states: uint16[n_events] ground truth)."""
+    scale, shift, drift, var, scale_sd, var_sd = params
+    states = kmer_walk(rng, n_events, p_stay, p_skip)
+    t = table[states].astype(np.float64)
+    mu, sigma, eta, sd_stdv = t[:, 0], t[:, 1], t[:, 2], t[:, 3]
+    lam = eta ** 3 / sd_stdv ** 2
+    length = np.maximum(0.002, rng.exponential(0.02, n_events))
+    start = np.concatenate([[0.0], np.cumsum(length)[:-1]])
+    mean = rng.normal(scale * mu + shift + drift * start, var * sigma)
+    stdv = rng.wald(scale_sd * eta, var_sd * lam)
+    stdv = np.clip(stdv, 1e-3, 4.0)
+    return {
+        "mean": mean.astype(np.float32),
+        "stdv": stdv.astype(np.float32),
+        "start": start.astype(np.float32),
+        "states": states,
+    }
+
+
+def make_batch(seed, table, lengths, params=None, p_stay=0.1, p_skip=0.3):
+    """Packed batch: concatenated float32 mean/stdv/start + uint64 offsets[n_reads+1].
+    params: None (identity for every read) or array[n_reads, 6]."""
+    rng = np.random.default_rng(seed)
+    lengths = np.asarray(lengths, dtype=np.int64)
+    off = np.zeros(lengths.size + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lengths)
+    total = int(off[-1])
+    mean = np.empty(total, np.float32)
+    stdv = np.empty(total, np.float32)
+    start = np.empty(total, np.float32)
+    truth = np.empty(total, np.uint16)
+    for r, n in enumerate(lengths):
+        p = IDENTITY_PARAMS if params is None else tuple(float(v) for v in params[r])
+        rd = make_read(rng, table, int(n), p, p_stay, p_skip)
+        a, b = int(off[r]), int(off[r + 1])
+        mean[a:b], stdv[a:b], start[a:b], truth[a:b] = rd["mean"], rd["stdv"], rd["start"], rd["states"]
+    return {"ev_off": off, "mean": mean, "stdv": stdv, "start": start, "truth": truth}
+
+
+def random_params(rng, n):
+    """Ground-truth scaling for the training configs."""
+    p = np.empty((n, 6), np.float32)
+    p[:, 0] = rng.uniform(0.9, 1.1, n)
+    p[:, 1] = rng.uniform(-5, 5, n)
+    p[:, 2] = rng.uniform(-0.005, 0.005, n)
+    p[:, 3] = rng.uniform(0.9, 1.3, n)
+    p[:, 4] = rng.uniform(0.8, 1.2, n)
+    p[:, 5] = rng.uniform(0.8, 1.5, n)
+    return p
