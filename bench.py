@@ -1,0 +1,308 @@
+#!/usr/bin/env python3
+"""bench.py -- Viterbi events/sec of the nanocall decoding hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--events E] [--impl ours|reference]
+
+A "step" is one pass of the hot path (scale + transitions + drift + Viterbi forward + traceback +
+moves) over one batch of synthetic reads.  Default workload = BASELINE.json configs[1]:
+10k reads x 10k events of R7.3 template, fixed identity scaling, default transitions, 1 B200.
+Under torchrun (N > 1) every rank decodes its own R reads on its own GPU (reads shard naturally,
+no data-path collective): scaling = "weak", value = all ranks' events / max-over-ranks time.
+
+JSON line keys beyond the base contract:
+  roofline      HBM view of the dominant kernel (viterbi_kernel): algorithmic bytes = 4112 B/event
+                (4096 B backpointers + 12 B event + 1 B traceback read + 3 B state/move)
+  roofline_fp32 the roofline that actually binds (FP32 issue): 245,600 FP32 op/event
+                against 148 SMs x 128 lanes x SM clock measured under load
+  cpu_baseline  the reference's own Viterbi (oracle/_ref, kind "reference"; the C port otherwise)
+                on a bounded sample of the same reads on this box's host cores
+  e2e           same metric through nc_viterbi_packed with pinned HOST buffers: H2D of the events
+                and D2H of states/moves/scores inside the timed region
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBM_BYTES_PER_EVENT = 4112
+FP32_OPS_PER_EVENT = 245600
+MODEL = "r73.t.006.ont.model"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads", type=int, default=10000, help="reads per GPU")
+    ap.add_argument("--events", type=int, default=10000, help="events per read")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-reads", type=int, default=0, help="0 = 2 per host thread")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+def host_threads_for_cpu_baseline(n_events):
+    """All host threads, bounded so the reference's 32 KiB/event matrices fit in RAM."""
+    cores = os.cpu_count() or 1
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        per_thread = n_events * 32768 + (64 << 20)
+        cores = max(1, min(cores, int(avail * 0.5 // per_thread)))
+    except Exception:
+        pass
+    return cores
+
+
+def cpu_baseline(table, batch, n_events, sample_reads=0):
+    """Time the reference's Viterbi on a bounded sample (first reads of the batch). test-infra import."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    threads = host_threads_for_cpu_baseline(n_events)
+    if oracle_lib.have_ref():
+        lib, kind = oracle_lib.ref(), "reference"
+    else:
+        lib, kind = oracle_lib.port(), "port"
+    n_reads = sample_reads or min(batch["ev_off"].size - 1, 2 * threads)
+    off = batch["ev_off"][:n_reads + 1]
+    tot = int(off[-1])
+    pm = np.tile(np.array([1, 0, 0, 1, 1, 1], np.float32), (n_reads, 1))
+    st = np.tile(np.array([0.1, 0.3], np.float32), (n_reads, 1))
+    t0 = time.perf_counter()
+    lib.viterbi_batch(table, off, batch["mean"][:tot], batch["stdv"][:tot], batch["start"][:tot], pm, st,
+                      n_threads=threads, want_paths=False)
+    dt = time.perf_counter() - t0
+    return {"value": tot / dt, "unit": "events/s", "cores": threads, "kind": kind,
+            "sample": f"{n_reads} reads x {n_events} events ({tot} events) in {dt:.1f} s, "
+                      f"{threads} threads, one read per worker (pfor chunk 1)"}, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU Viterbi on the box's host cores."""
+    if rank != 0:
+        return
+    from nanocall_b200 import synth, models
+    table = models.builtin_model(MODEL)["table"]
+    threads = host_threads_for_cpu_baseline(args.events)
+    n_reads = args.cpu_sample_reads or min(args.reads, 2 * threads)
+    batch = synth.make_batch_uniform(args.seed, table, n_reads, args.events)
+    times = []
+    res = None
+    for it in range(args.warmup + args.steps):
+        res, dt = cpu_baseline(table, batch, args.events, n_reads)
+        if it >= args.warmup:
+            times.append(dt)
+        if sum(times) > 240:  # keep the whole run within a few minutes
+            break
+    tot = n_reads * args.events
+    v = tot * len(times) / sum(times)
+    res["value"] = v
+    line = {"impl": "reference", "metric": "viterbi_events_per_sec", "value": v, "unit": "events/s",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.reads} reads x {args.events} events R7.3 template, Viterbi only "
+                                   f"(configs[1]); each step = bounded sample of {n_reads} reads",
+                       "model": MODEL},
+            "cpu_baseline": res,
+            "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from nanocall_b200 import api, synth, models
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: nanocall_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    table = models.builtin_model(MODEL)["table"]
+    batch = synth.make_batch_uniform(args.seed + rank, table, args.reads, args.events)
+    total = args.reads * args.events
+    lstd = np.log(np.where(batch["stdv"] == 0, np.float32(0.01), batch["stdv"])).astype(np.float32)
+
+    ctx = api.Context(local_rank)
+    mid = ctx.register_model(table, 0)
+    info = ctx.device_info()
+
+    # pinned host copies (e2e) and device-resident copies (value)
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in
+            (("mean", batch["mean"]), ("stdv", batch["stdv"]), ("start", batch["start"]), ("lstd", lstd))}
+    d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    d_states = torch.empty(total, dtype=torch.int16, device=dev)
+    d_moves = torch.empty(total, dtype=torch.uint8, device=dev)
+    h_states = torch.empty(total, dtype=torch.int16).pin_memory()
+    h_moves = torch.empty(total, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step_device():
+        return ctx.viterbi_device(batch["ev_off"], d["mean"].data_ptr(), d["stdv"].data_ptr(), d["start"].data_ptr(),
+                                  d["lstd"].data_ptr(), mid, d_states=d_states.data_ptr(), d_moves=d_moves.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    path = None
+    for _ in range(args.steps):
+        path = step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag.set()
+    sampler.join()
+    clocks = sampler.summary()
+
+    # e2e: pinned host buffers in, host results out, wall clock around the public call
+    e2e = None
+    if not args.no_e2e:
+        hp = {k: v.numpy() for k, v in host.items()}
+        hs, hm = h_states.numpy().view(np.uint16), h_moves.numpy()
+        lib = ctx.lib
+        n = args.reads
+        midv = np.full(n, mid, np.int32)
+        pm_a, st_a = api._pm_array(None, n), api._st_array(None, n)
+        pathv = np.zeros(n, np.float32)
+
+        def step_host():
+            ctx._check(lib.nc_viterbi_packed(ctx.h, n, batch["ev_off"].ctypes.data, hp["mean"].ctypes.data,
+                                             hp["stdv"].ctypes.data, hp["start"].ctypes.data, hp["lstd"].ctypes.data,
+                                             midv.ctypes.data, pm_a.ctypes.data, st_a.ctypes.data, 0,
+                                             pathv.ctypes.data, hs.ctypes.data, hm.ctypes.data))
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if not np.array_equal(pathv.view(np.uint32), path.view(np.uint32)):
+            raise SystemExit("e2e and device-resident paths disagree")
+        e2e = (e2e_s, total * 16 + n * (288 + 4), total * 3 + n * 4)
+
+    if world > 1:
+        tt = torch.tensor([ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt[0])
+        if e2e:
+            e2e = (float(tt[1]),) + e2e[1:]
+
+    if rank == 0:
+        ms_per_step = ms / args.steps
+        value = world * total / (ms_per_step * 1e-3)
+        hbm_peak, peak_kind = peaks()
+        per_gpu_evs = total / (ms_per_step * 1e-3)
+        ach_gbs = per_gpu_evs * HBM_BYTES_PER_EVENT / 1e9
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        fp32_peak = info["n_sms"] * 128 * sm_mhz * 1e6 / 1e12  # T FP32 instr/s (non-FMA issue)
+        line = {
+            "metric": "viterbi_events_per_sec", "value": value, "unit": "events/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.reads} reads x {args.events} events per GPU, R7.3 template, "
+                                   "fixed identity scaling, default transitions, Viterbi + traceback (configs[1])",
+                       "model": MODEL, "reads_per_gpu": args.reads, "events_per_read": args.events,
+                       "l2": "inputs (1.6 GB events + 41 MB backpointers per read) larger than L2",
+                       "device": info["name"], "n_sms": info["n_sms"]},
+            "clocks": clocks,
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                         "kernel": "viterbi_kernel", "algorithmic_bytes_per_event": HBM_BYTES_PER_EVENT},
+            "roofline_fp32": {"bound": "fp32_issue", "achieved": per_gpu_evs * FP32_OPS_PER_EVENT / 1e12,
+                              "peak": fp32_peak, "unit": "Tinstr/s", "frac": per_gpu_evs * FP32_OPS_PER_EVENT / 1e12 / fp32_peak,
+                              "algorithmic_ops_per_event": FP32_OPS_PER_EVENT,
+                              "peak_kind": f"{info['n_sms']} SMs x 128 lanes x {sm_mhz:.0f} MHz under load"},
+        }
+        if e2e:
+            line["e2e"] = {"value": world * total * args.steps / e2e[0], "unit": "events/s",
+                           "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
+                           "timing": "wall clock around nc_viterbi_packed(NC_MEM_HOST), pinned buffers"}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_baseline(table, batch, args.events, args.cpu_sample_reads)
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

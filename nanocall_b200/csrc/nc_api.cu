@@ -1,0 +1,385 @@
+// C ABI of nanocall_b200 (include/nanocall_b200.h): context, model registry, batch dispatch.
+// No CPU fallback lives here: without a CUDA device nc_ctx_create fails and nothing else runs.
+#include "nc_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+static thread_local std::string g_create_error;
+
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct nc_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop;
+    std::vector< nc::HostModel > models;
+    float* d_models = nullptr;
+    int d_models_cap = 0;
+    unsigned char* d_bp = nullptr;
+    size_t bp_bytes = 0;
+    float* d_logsum_tbl = nullptr;
+    std::string err;
+    // grow-only scratch
+    DevBuf jobs, order, counter, path, mean, stdv, start, lstd, states, moves;
+    DevBuf fb_alpha, fb_beta, fb_misc;
+    unsigned host_threads = 1;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_kernel_ms = 0.f;
+};
+
+#define NC_FAIL(ctx, code, ...)                                        \
+    do {                                                               \
+        char _b[512];                                                  \
+        std::snprintf(_b, sizeof _b, __VA_ARGS__);                     \
+        (ctx)->err = _b;                                               \
+        return (code);                                                 \
+    } while (0)
+
+#define NC_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            NC_FAIL(ctx, NC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static int dev_reserve(nc_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return NC_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        NC_FAIL(ctx, NC_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return NC_OK;
+}
+static void dev_free(DevBuf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+extern "C" {
+
+int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
+{
+    if (!out) { g_create_error = "nc_ctx_create: out is NULL"; return NC_ERR_ARG; }
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+    {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (nanocall_b200 has no CPU fallback)";
+        cudaGetLastError();
+        return NC_ERR_CUDA;
+    }
+    if (device < 0 || device >= n_dev) { g_create_error = "nc_ctx_create: bad device index"; return NC_ERR_ARG; }
+    nc_ctx* ctx = new nc_ctx();
+    ctx->device = device;
+    auto fail = [&](const char* what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        nc_ctx_destroy(ctx);
+        return NC_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if (bp_pool_bytes == 0)
+    {
+        size_t free_b = 0, total_b = 0;
+        if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return fail("cudaMemGetInfo", e);
+        bp_pool_bytes = std::min< size_t >(free_b / 2, (size_t)64 << 30);
+    }
+    bp_pool_bytes &= ~(size_t)4095;
+    if ((e = cudaMalloc(&ctx->d_bp, bp_pool_bytes)) != cudaSuccess) return fail("cudaMalloc(backpointer pool)", e);
+    ctx->bp_bytes = bp_pool_bytes;
+    if ((e = cudaFuncSetAttribute(nc::viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)nc::viterbi_smem_bytes())) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(viterbi_kernel)", e);
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    unsigned hc = std::thread::hardware_concurrency();
+    ctx->host_threads = hc ? std::min(hc, 32u) : 4u;
+    *out = ctx;
+    return NC_OK;
+}
+
+void nc_ctx_destroy(nc_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : { &ctx->jobs, &ctx->order, &ctx->counter, &ctx->path, &ctx->mean, &ctx->stdv, &ctx->start,
+                       &ctx->lstd, &ctx->states, &ctx->moves, &ctx->fb_alpha, &ctx->fb_beta, &ctx->fb_misc })
+        dev_free(*b);
+    if (ctx->d_models) cudaFree(ctx->d_models);
+    if (ctx->d_bp) cudaFree(ctx->d_bp);
+    if (ctx->d_logsum_tbl) cudaFree(ctx->d_logsum_tbl);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* nc_last_error(const nc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+void* nc_ctx_stream(nc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+float nc_ctx_last_kernel_ms(nc_ctx* ctx) { return ctx ? ctx->last_kernel_ms : -1.f; }
+
+int nc_ctx_sync(nc_ctx* ctx)
+{
+    if (!ctx) return NC_ERR_ARG;
+    NC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NC_OK;
+}
+
+int nc_ctx_device_info(nc_ctx* ctx, int* n_sms, size_t* total_mem, char* name, int name_cap)
+{
+    if (!ctx) return NC_ERR_ARG;
+    if (n_sms) *n_sms = ctx->prop.multiProcessorCount;
+    if (total_mem) *total_mem = ctx->prop.totalGlobalMem;
+    if (name && name_cap > 0) { std::strncpy(name, ctx->prop.name, name_cap - 1); name[name_cap - 1] = 0; }
+    return NC_OK;
+}
+
+int nc_model_register(nc_ctx* ctx, const float* table, int strand, int* model_id)
+{
+    if (!ctx) return NC_ERR_ARG;
+    if (!table || !model_id || strand < 0 || strand > 2) NC_FAIL(ctx, NC_ERR_ARG, "nc_model_register: bad argument");
+    NC_CUDA(ctx, cudaSetDevice(ctx->device));
+    nc::HostModel m;
+    nc::host_model_prepare(table, m);
+    m.strand = strand;
+    int id = (int)ctx->models.size();
+    if (id + 1 > ctx->d_models_cap)
+    {
+        int cap = std::max(8, ctx->d_models_cap * 2);
+        float* nd = nullptr;
+        NC_CUDA(ctx, cudaMalloc(&nd, (size_t)cap * nc::MODEL_FLOATS * sizeof(float)));
+        if (ctx->d_models)
+        {
+            NC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            NC_CUDA(ctx, cudaMemcpy(nd, ctx->d_models, (size_t)id * nc::MODEL_FLOATS * sizeof(float), cudaMemcpyDeviceToDevice));
+            cudaFree(ctx->d_models);
+        }
+        ctx->d_models = nd;
+        ctx->d_models_cap = cap;
+    }
+    std::vector< float > blob(nc::MODEL_FLOATS);
+    const std::vector< float >* parts[6] = { &m.level_mean, &m.level_stdv, &m.sd_mean, &m.sd_lambda, &m.log_level_stdv, &m.log_sd_lambda };
+    for (int a = 0; a < 6; ++a) std::memcpy(blob.data() + (size_t)a * NC_N_STATES, parts[a]->data(), NC_N_STATES * sizeof(float));
+    NC_CUDA(ctx, cudaMemcpy(ctx->d_models + (size_t)id * nc::MODEL_FLOATS, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->models.push_back(std::move(m));
+    *model_id = id;
+    return NC_OK;
+}
+
+int nc_model_stats(nc_ctx* ctx, int model_id, float* mean, float* stdv)
+{
+    if (!ctx) return NC_ERR_ARG;
+    if (model_id < 0 || model_id >= (int)ctx->models.size()) NC_FAIL(ctx, NC_ERR_ARG, "nc_model_stats: unknown model id %d", model_id);
+    if (mean) *mean = ctx->models[model_id].mean;
+    if (stdv) *stdv = ctx->models[model_id].stdv;
+    return NC_OK;
+}
+
+int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
+                      const float* mean, const float* stdv, const float* start, const float* log_stdv,
+                      const int32_t* model_id, const nc_pm_params* pm, const nc_st_params* st,
+                      nc_mem mem, float* path_logprob, uint16_t* states, uint8_t* moves)
+{
+    if (!ctx) return NC_ERR_ARG;
+    if (n_jobs == 0) return NC_OK;
+    if (!ev_off || !mean || !stdv || !start || !model_id || !pm || !st || !path_logprob)
+        NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_packed: NULL argument");
+    if (mem == NC_MEM_DEVICE && !log_stdv)
+        NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_packed: log_stdv is required for device-resident events");
+    if (moves && !states && mem == NC_MEM_DEVICE)
+        NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_packed: moves need states for device-resident outputs");
+    if (ctx->models.empty()) NC_FAIL(ctx, NC_ERR_STATE, "nc_viterbi_packed: no model registered");
+    NC_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    // ---- job descriptors (host): scalars, logs, transition LUTs; longest-first order
+    const uint64_t total = ev_off[n_jobs] - ev_off[0];
+    std::vector< nc::DevJob > jobs(n_jobs);
+    uint32_t max_len = 0;
+    {
+        float lut_key[2] = { -1.f, -1.f };
+        float lut_val[64];
+        for (uint32_t k = 0; k < n_jobs; ++k)
+        {
+            if (ev_off[k + 1] <= ev_off[k]) NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_packed: job %u has no events", k);
+            uint64_t len = ev_off[k + 1] - ev_off[k];
+            if (len > 0xffffffffull) NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_packed: job %u too long", k);
+            if (model_id[k] < 0 || model_id[k] >= (int)ctx->models.size())
+                NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_packed: job %u: unknown model id %d", k, model_id[k]);
+            nc::DevJob& J = jobs[k];
+            J.ev_off = ev_off[k] - ev_off[0];
+            J.n_events = (unsigned)len;
+            J.model = model_id[k];
+            J.scale = pm[k].scale; J.shift = pm[k].shift; J.drift = pm[k].drift;
+            J.var = pm[k].var; J.scale_sd = pm[k].scale_sd; J.var_sd = pm[k].var_sd;
+            nc::host_job_logs(pm[k], J.log_var, J.log_var_sd);
+            if (st[k].p_stay != lut_key[0] || st[k].p_skip != lut_key[1])
+            {
+                nc_transition_lut(st[k].p_stay, st[k].p_skip, lut_val);
+                lut_key[0] = st[k].p_stay;
+                lut_key[1] = st[k].p_skip;
+            }
+            std::memcpy(J.lut, lut_val, sizeof lut_val);
+            max_len = std::max(max_len, J.n_events);
+        }
+    }
+    std::vector< unsigned > order(n_jobs);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return jobs[a].n_events > jobs[b].n_events; });
+
+    const size_t slab = (size_t)max_len * NC_N_STATES;
+    size_t max_ctas = ctx->bp_bytes / slab;
+    if (max_ctas == 0)
+        NC_FAIL(ctx, NC_ERR_NOMEM, "nc_viterbi_packed: a %u-event job needs %zu backpointer bytes, pool has %zu",
+                max_len, slab, ctx->bp_bytes);
+    unsigned grid = (unsigned)std::min< size_t >(std::min< size_t >(n_jobs, (size_t)ctx->prop.multiProcessorCount), max_ctas);
+
+    int rc;
+    if ((rc = dev_reserve(ctx, ctx->jobs, n_jobs * sizeof(nc::DevJob))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->order, n_jobs * sizeof(unsigned))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->counter, sizeof(unsigned))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->path, n_jobs * sizeof(float))) != NC_OK) return rc;
+    cudaStream_t s = ctx->stream;
+    NC_CUDA(ctx, cudaMemcpyAsync(ctx->jobs.p, jobs.data(), n_jobs * sizeof(nc::DevJob), cudaMemcpyHostToDevice, s));
+    NC_CUDA(ctx, cudaMemcpyAsync(ctx->order.p, order.data(), n_jobs * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+    NC_CUDA(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), s));
+
+    nc::VitArgs a;
+    a.jobs = (const nc::DevJob*)ctx->jobs.p;
+    a.order = (const unsigned*)ctx->order.p;
+    a.n_jobs = n_jobs;
+    a.next_job = (unsigned*)ctx->counter.p;
+    a.models = ctx->d_models;
+    a.bp_pool = ctx->d_bp;
+    a.slab_bytes = slab;
+    a.path_logprob = (float*)ctx->path.p;
+    a.log_2pi = (float)std::log(2.0 * M_PI);
+    a.log_n_states = std::log((float)NC_N_STATES);
+
+    std::vector< float > lstd_host;
+    const uint64_t base = ev_off[0];
+    if (mem == NC_MEM_HOST)
+    {
+        const float* lsp = log_stdv ? log_stdv + base : nullptr;
+        if (!lsp)
+        {
+            lstd_host.resize(total);
+            nc::host_event_logs(total, stdv + base, lstd_host.data(), ctx->host_threads);
+            lsp = lstd_host.data();
+        }
+        if ((rc = dev_reserve(ctx, ctx->mean, total * sizeof(float))) != NC_OK) return rc;
+        if ((rc = dev_reserve(ctx, ctx->stdv, total * sizeof(float))) != NC_OK) return rc;
+        if ((rc = dev_reserve(ctx, ctx->start, total * sizeof(float))) != NC_OK) return rc;
+        if ((rc = dev_reserve(ctx, ctx->lstd, total * sizeof(float))) != NC_OK) return rc;
+        NC_CUDA(ctx, cudaMemcpyAsync(ctx->mean.p, mean + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
+        NC_CUDA(ctx, cudaMemcpyAsync(ctx->stdv.p, stdv + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
+        NC_CUDA(ctx, cudaMemcpyAsync(ctx->start.p, start + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
+        NC_CUDA(ctx, cudaMemcpyAsync(ctx->lstd.p, lsp, total * sizeof(float), cudaMemcpyHostToDevice, s));
+        a.mean = (const float*)ctx->mean.p;
+        a.stdv = (const float*)ctx->stdv.p;
+        a.start = (const float*)ctx->start.p;
+        a.log_stdv = (const float*)ctx->lstd.p;
+        a.states = nullptr;
+        a.moves = nullptr;
+        if (states || moves)
+        {
+            if ((rc = dev_reserve(ctx, ctx->states, total * sizeof(uint16_t))) != NC_OK) return rc;
+            a.states = (unsigned short*)ctx->states.p;
+        }
+        if (moves)
+        {
+            if ((rc = dev_reserve(ctx, ctx->moves, total)) != NC_OK) return rc;
+            a.moves = (unsigned char*)ctx->moves.p;
+        }
+    }
+    else
+    {
+        a.mean = mean + base;
+        a.stdv = stdv + base;
+        a.start = start + base;
+        a.log_stdv = log_stdv + base;
+        a.states = states ? states + base : nullptr;
+        a.moves = moves ? moves + base : nullptr;
+    }
+
+    NC_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    nc::viterbi_kernel<<< grid, nc::VIT_THREADS, nc::viterbi_smem_bytes(), s >>>(a);
+    NC_CUDA(ctx, cudaGetLastError());
+    NC_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+
+    NC_CUDA(ctx, cudaMemcpyAsync(path_logprob, ctx->path.p, n_jobs * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (mem == NC_MEM_HOST)
+    {
+        if (states) NC_CUDA(ctx, cudaMemcpyAsync(states + base, ctx->states.p, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+        if (moves) NC_CUDA(ctx, cudaMemcpyAsync(moves + base, ctx->moves.p, total, cudaMemcpyDeviceToHost, s));
+    }
+    NC_CUDA(ctx, cudaStreamSynchronize(s));
+    NC_CUDA(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
+    return NC_OK;
+}
+
+int nc_viterbi_batch(nc_ctx* ctx, uint32_t n_jobs, const nc_vit_job* jobs, nc_vit_out* outs)
+{
+    if (!ctx) return NC_ERR_ARG;
+    if (n_jobs == 0) return NC_OK;
+    if (!jobs || !outs) NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_batch: NULL argument");
+    std::vector< uint64_t > off(n_jobs + 1, 0);
+    for (uint32_t k = 0; k < n_jobs; ++k)
+    {
+        if (jobs[k].n_events == 0 || !jobs[k].mean || !jobs[k].stdv || !jobs[k].start)
+            NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_batch: job %u is empty or has NULL events", k);
+        off[k + 1] = off[k] + jobs[k].n_events;
+    }
+    const uint64_t total = off[n_jobs];
+    std::vector< float > mean(total), stdv(total), start(total), path(n_jobs);
+    std::vector< int32_t > mid(n_jobs);
+    std::vector< nc_pm_params > pm(n_jobs);
+    std::vector< nc_st_params > st(n_jobs);
+    std::vector< uint16_t > states(total);
+    std::vector< uint8_t > moves(total);
+    for (uint32_t k = 0; k < n_jobs; ++k)
+    {
+        std::memcpy(mean.data() + off[k], jobs[k].mean, jobs[k].n_events * sizeof(float));
+        std::memcpy(stdv.data() + off[k], jobs[k].stdv, jobs[k].n_events * sizeof(float));
+        std::memcpy(start.data() + off[k], jobs[k].start, jobs[k].n_events * sizeof(float));
+        mid[k] = jobs[k].model_id;
+        pm[k] = jobs[k].pm;
+        st[k] = jobs[k].st;
+    }
+    int rc = nc_viterbi_packed(ctx, n_jobs, off.data(), mean.data(), stdv.data(), start.data(), nullptr,
+                               mid.data(), pm.data(), st.data(), NC_MEM_HOST, path.data(), states.data(), moves.data());
+    if (rc != NC_OK) return rc;
+    for (uint32_t k = 0; k < n_jobs; ++k)
+    {
+        outs[k].path_logprob = path[k];
+        if (outs[k].states) std::memcpy(outs[k].states, states.data() + off[k], jobs[k].n_events * sizeof(uint16_t));
+        if (outs[k].moves) std::memcpy(outs[k].moves, moves.data() + off[k], jobs[k].n_events);
+        outs[k].n_bases = nc_base_seq(jobs[k].n_events, states.data() + off[k], moves.data() + off[k],
+                                      outs[k].bases, outs[k].bases ? outs[k].bases_cap : 0);
+    }
+    return NC_OK;
+}
+
+} // extern "C"

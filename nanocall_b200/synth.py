@@ -79,3 +79,35 @@ def random_params(rng, n):
     p[:, 4] = rng.uniform(0.8, 1.2, n)
     p[:, 5] = rng.uniform(0.8, 1.5, n)
     return p
+
+
+def make_batch_uniform(seed, table, n_reads, n_events, p_stay=0.1, p_skip=0.3):
+    """Vectorised generator for n_reads reads of exactly n_events events, identity scaling (bench
+    workloads: 10k x 10k).  One long stay/step/skip walk over a random base stream is cut into
+    reads; `start` restarts at 0 in every read."""
+    rng = np.random.default_rng(seed)
+    total = n_reads * n_events
+    u = rng.random(total, dtype=np.float32)
+    move = np.where(u < p_stay, 0, np.where(u < 1.0 - p_skip, 1, 2)).astype(np.int64)
+    del u
+    move[0] = 0
+    pos = np.cumsum(move)
+    del move
+    bases = rng.integers(0, 4, size=int(pos[-1]) + 6, dtype=np.uint16)
+    kmer = np.zeros(bases.size - 5, dtype=np.uint16)
+    for k in range(6):
+        kmer = (kmer << 2) | bases[k:k + kmer.size]
+    states = kmer[pos]
+    del pos, bases, kmer
+    t = table[states]
+    mu, sigma = t[:, 0], t[:, 1]
+    eta = t[:, 2].astype(np.float64)
+    lam = eta ** 3 / t[:, 3].astype(np.float64) ** 2
+    mean = (mu + sigma * rng.standard_normal(total, dtype=np.float32)).astype(np.float32)
+    stdv = np.clip(rng.wald(eta, lam), 1e-3, 4.0).astype(np.float32)
+    del eta, lam, t
+    length = np.maximum(0.002, rng.exponential(0.02, total)).reshape(n_reads, n_events)
+    start = np.cumsum(length, axis=1) - length
+    off = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(n_events))
+    return {"ev_off": off, "mean": mean, "stdv": stdv, "start": start.astype(np.float32).reshape(-1),
+            "truth": states}
