@@ -11,69 +11,9 @@
 #include <thread>
 #include <vector>
 
-static thread_local std::string g_create_error;
+#include "nc_ctx.h"
 
-struct DevBuf
-{
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
-struct nc_ctx
-{
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaDeviceProp prop;
-    std::vector< nc::HostModel > models;
-    float* d_models = nullptr;
-    int d_models_cap = 0;
-    unsigned char* d_bp = nullptr;
-    size_t bp_bytes = 0;
-    float* d_logsum_tbl = nullptr;
-    std::string err;
-    // grow-only scratch
-    DevBuf jobs, order, counter, path, mean, stdv, start, lstd, states, moves;
-    DevBuf fb_alpha, fb_beta, fb_misc;
-    unsigned host_threads = 1;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_kernel_ms = 0.f;
-};
-
-#define NC_FAIL(ctx, code, ...)                                        \
-    do {                                                               \
-        char _b[512];                                                  \
-        std::snprintf(_b, sizeof _b, __VA_ARGS__);                     \
-        (ctx)->err = _b;                                               \
-        return (code);                                                 \
-    } while (0)
-
-#define NC_CUDA(ctx, call)                                                                   \
-    do {                                                                                     \
-        cudaError_t _e = (call);                                                             \
-        if (_e != cudaSuccess)                                                               \
-            NC_FAIL(ctx, NC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
-    } while (0)
-
-static int dev_reserve(nc_ctx* ctx, DevBuf& b, size_t bytes)
-{
-    if (bytes <= b.cap) return NC_OK;
-    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&b.p, want);
-    if (e != cudaSuccess)
-    {
-        cudaGetLastError();
-        NC_FAIL(ctx, NC_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
-    }
-    b.cap = want;
-    return NC_OK;
-}
-static void dev_free(DevBuf& b)
-{
-    if (b.p) cudaFree(b.p);
-    b.p = nullptr;
-    b.cap = 0;
-}
+thread_local std::string g_create_error;
 
 extern "C" {
 
@@ -125,11 +65,13 @@ void nc_ctx_destroy(nc_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : { &ctx->jobs, &ctx->order, &ctx->counter, &ctx->path, &ctx->mean, &ctx->stdv, &ctx->start,
-                       &ctx->lstd, &ctx->states, &ctx->moves, &ctx->fb_alpha, &ctx->fb_beta, &ctx->fb_misc })
+                       &ctx->lstd, &ctx->states, &ctx->moves, &ctx->fb_scratch, &ctx->fb_seqs, &ctx->fb_groups, &ctx->fb_jobs,
+                       &ctx->fb_lz, &ctx->fb_pm, &ctx->fb_st, &ctx->fb_counter, &ctx->fb_mean, &ctx->fb_stdv, &ctx->fb_start, &ctx->fb_lstd })
         dev_free(*b);
     if (ctx->d_models) cudaFree(ctx->d_models);
     if (ctx->d_bp) cudaFree(ctx->d_bp);
     if (ctx->d_logsum_tbl) cudaFree(ctx->d_logsum_tbl);
+    if (ctx->d_train_kmers) cudaFree(ctx->d_train_kmers);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -1,0 +1,80 @@
+// Context object and error plumbing shared by the ABI translation units.
+#ifndef NC_CTX_H
+#define NC_CTX_H
+
+#include "nc_kernels.h"
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+extern thread_local std::string g_create_error;
+
+
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct nc_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop;
+    std::vector< nc::HostModel > models;
+    float* d_models = nullptr;
+    int d_models_cap = 0;
+    unsigned char* d_bp = nullptr;
+    size_t bp_bytes = 0;
+    float* d_logsum_tbl = nullptr;
+    std::string err;
+    // grow-only scratch
+    DevBuf jobs, order, counter, path, mean, stdv, start, lstd, states, moves;
+    DevBuf fb_scratch, fb_seqs, fb_groups, fb_jobs, fb_lz, fb_pm, fb_st, fb_counter, fb_mean, fb_stdv, fb_start, fb_lstd;
+    unsigned* d_train_kmers = nullptr;
+    unsigned n_train_kmers = 0;
+    size_t fb_scratch_limit = 0;  // bytes of E|alpha|beta slabs per wave (0 = pick from free memory)
+    unsigned host_threads = 1;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_kernel_ms = 0.f;
+};
+
+#define NC_FAIL(ctx, code, ...)                                        \
+    do {                                                               \
+        char _b[512];                                                  \
+        std::snprintf(_b, sizeof _b, __VA_ARGS__);                     \
+        (ctx)->err = _b;                                               \
+        return (code);                                                 \
+    } while (0)
+
+#define NC_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            NC_FAIL(ctx, NC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+inline int dev_reserve(nc_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return NC_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        NC_FAIL(ctx, NC_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return NC_OK;
+}
+inline void dev_free(DevBuf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+
+#endif

@@ -1,17 +1,552 @@
-// K2 (Forward/Backward + trainer statistics): under construction; the entry points exist so the
-// ABI is complete, and fail loudly rather than fall back to anything.
+// K2: log-space Forward/Backward (Forward_Backward.hpp:46-135) and the sufficient statistics of
+// Parameter_Trainer (Parameter_Trainer.hpp:230-532) for batches of training sequences.
+//
+// Bit-exactness.  alpha, beta and log Pr[data] reproduce the reference bit for bit.  That needs
+//   * p7_FLogsum literally (logsum.hpp:141-154): max, min, the test `min == -inf || max-min >= 15.999f`,
+//     index (int)((max-min)*1000.f), the 16000-entry table built on the host in double (logsum.hpp:113-127);
+//   * the reference's accumulation ORDER: from -inf, over the ascending merged predecessor list from_v(j)
+//     (forward) / successor list to_v(j) (backward), each edge with its exact weight.
+// The lists are never materialised.  Predecessors of j sorted by index fall into 16 "slots" (index >> 8):
+// slot s holds the two-step predecessor (s<<8)|(j>>4), the one-step predecessor (b<<10)|(j>>2) when
+// s == 4b + (j>>10), and j itself when s == j>>8; inside a slot the order is that of the low bytes.
+// Successors of j are two contiguous blocks, [(j&255)<<4, +16) and [(j&1023)<<2, +4), plus j.  An index that
+// occurs twice is ONE edge in the reference (std::set union, State_Transitions.hpp:205-209) whose weight
+// carries every matching overlap term; here the lower-class duplicate is replaced by -inf, and
+// p7_FLogsum(x, -inf) == x exactly, so the chain is the reference's chain.
+//
+// Kernels (one wave = the sequences whose E/alpha/beta slabs fit the scratch pool):
+//   emission_kernel   E[i][j] = log_pr_corrected_emission(j, e_i) for every sequence (grid: seq x event tiles)
+//   fwbw_kernel       one CTA per sequence: forward, backward, log Pr[data]; alpha/beta to the slabs
+//   pm_stats_kernel   per event the six posterior-weighted sums of train_pm_params (:263-296)
+//   st_stats_kernel   one CTA per (group, strand): the three log-space accumulators of train_st_params (:471-514),
+//                     folded sequentially in the reference's (sequence, event, k-mer) order
+// The 3x3 solve, the clamps and exp() of the final ratios run on the host in nc_train.cpp.
+#include "nc_device.cuh"
 #include "nc_kernels.h"
-#include <string>
 
-extern "C" {
-int nc_fwbw(nc_ctx*, int32_t, const nc_pm_params*, const nc_st_params*, uint32_t, const float*, const float*,
-            const float*, float*, float*, float*)
+namespace nc {
+
+namespace {
+
+constexpr int FB_THREADS = 512;
+constexpr int FB_SPT = 8;
+constexpr int COL_PAD_SHIFT = 4;  // phys(n) = n + 4 * (n >> 4): conflict-free 16-float block reads
+constexpr int COL_FLOATS = NC_N_STATES + 4 * (NC_N_STATES >> COL_PAD_SHIFT);  // 5120
+
+__device__ __forceinline__ int cphys(int n) { return n + ((n >> COL_PAD_SHIFT) << 2); }
+
+// p7_FLogsum (logsum.hpp:141-154)
+__device__ __forceinline__ float flogsum(float a, float b, const float* __restrict__ tbl)
 {
-    return NC_ERR_STATE;
+    const float mx = (a > b) ? a : b;
+    const float mn = (a < b) ? a : b;
+    const float d = __fsub_rn(mx, mn);
+    const bool plain = (mn == NC_NEG_INF) || (d >= 15.999f);
+    int idx = (int)__fmul_rn(d, 1000.0f);
+    idx = plain ? 0 : idx;
+    const float r = __fadd_rn(mx, tbl[idx]);
+    return plain ? mx : r;
 }
-int nc_train_round_batch(nc_ctx*, uint32_t, const uint32_t*, const uint64_t*, const uint8_t*, const float*,
-                         const float*, const float*, const nc_train_in*, const nc_train_opts*, nc_train_out*)
+
+struct StSmem
 {
-    return NC_ERR_STATE;
+    float tbl[16000];
+    float term[3][FB_THREADS];
+    float accs[4];
+};
+
+struct FbSmem
+{
+    float tbl[16000];
+    float col[2][COL_FLOATS];
+    float red[FB_THREADS / 32];
+    unsigned item;
+};
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// E[seq][i][j]
+__global__ void __launch_bounds__(FB_THREADS) emission_kernel(const FbArgs a)
+{
+    const unsigned seq = blockIdx.y;
+    const FbSeq& Q = a.seqs[seq];
+    const unsigned i0 = blockIdx.x * FB_EV_TILE;
+    if (i0 >= Q.n_events) return;
+    const DevJob& J = a.jobs[Q.job];
+    const int t = threadIdx.x;
+    const unsigned j0 = FB_SPT * t;
+    const float* M = a.models + (size_t)J.model * MODEL_FLOATS;
+    float* E = a.scratch + Q.slab + 0 * (size_t)Q.n_events * NC_N_STATES;
+    const unsigned i1 = min(i0 + FB_EV_TILE, Q.n_events);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half)
+    {
+        StateParams P[4];
+        const unsigned jb = j0 + 4 * half;
+        {
+            const float4 lm = __ldg(reinterpret_cast< const float4* >(M + 0 * NC_N_STATES + jb));
+            const float4 ls = __ldg(reinterpret_cast< const float4* >(M + 1 * NC_N_STATES + jb));
+            const float4 sm = __ldg(reinterpret_cast< const float4* >(M + 2 * NC_N_STATES + jb));
+            const float4 sl = __ldg(reinterpret_cast< const float4* >(M + 3 * NC_N_STATES + jb));
+            const float4 ll = __ldg(reinterpret_cast< const float4* >(M + 4 * NC_N_STATES + jb));
+            const float4 lsl = __ldg(reinterpret_cast< const float4* >(M + 5 * NC_N_STATES + jb));
+            P[0] = scale_state(lm.x, ls.x, sm.x, sl.x, ll.x, lsl.x, J, a.log_2pi);
+            P[1] = scale_state(lm.y, ls.y, sm.y, sl.y, ll.y, lsl.y, J, a.log_2pi);
+            P[2] = scale_state(lm.z, ls.z, sm.z, sl.z, ll.z, lsl.z, J, a.log_2pi);
+            P[3] = scale_state(lm.w, ls.w, sm.w, sl.w, ll.w, lsl.w, J, a.log_2pi);
+        }
+        for (unsigned i = i0; i < i1; ++i)
+        {
+            const unsigned long long e = Q.ev_off + i;
+            const float stdv = __ldg(a.stdv + e);
+            const float y = (stdv == 0.0f) ? 0.01f : stdv;                                  // Event.hpp:39-42
+            const float x = __fsub_rn(__ldg(a.mean + e), __fmul_rn(J.drift, __ldg(a.start + e)));  // Event.hpp:81
+            const float ly3 = __fmul_rn(3.0f, __ldg(a.log_stdv + e));
+            const float ry = __frcp_rn(y);
+            float4 o;
+            o.x = emission(P[0], x, y, ly3, ry, a.log_2pi);
+            o.y = emission(P[1], x, y, ly3, ry, a.log_2pi);
+            o.z = emission(P[2], x, y, ly3, ry, a.log_2pi);
+            o.w = emission(P[3], x, y, ly3, ry, a.log_2pi);
+            *reinterpret_cast< float4* >(E + (size_t)i * NC_N_STATES + jb) = o;
+        }
+    }
 }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FbSmem& sm = *reinterpret_cast< FbSmem* >(smem_raw);
+    const int t = threadIdx.x;
+    const int lane = t & 31;
+    for (int q = t; q < 16000; q += FB_THREADS) sm.tbl[q] = a.logsum_tbl[q];
+    const float* tbl = sm.tbl;
+
+    for (;;)
+    {
+        __syncthreads();
+        if (t == 0) sm.item = atomicAdd(a.next_item, 1u);
+        __syncthreads();
+        const unsigned seq = sm.item;
+        if (seq >= a.n_seqs) break;
+        const FbSeq& Q = a.seqs[seq];
+        const DevJob& J = a.jobs[Q.job];
+        const unsigned n = Q.n_events;
+        const float* E = a.scratch + Q.slab;
+        float* AL = a.scratch + Q.slab + 1 * (size_t)n * NC_N_STATES;
+        float* BE = a.scratch + Q.slab + 2 * (size_t)n * NC_N_STATES;
+
+        // =========================== forward (Forward_Backward.hpp:58-89); thread owns j = 8t .. 8t+7
+        {
+            const unsigned j0 = FB_SPT * t;
+            const unsigned g = t >> 1;
+            const float wT = J.lut[trans_mask(g, j0) & 0x3cu];
+            float wO[2];
+            wO[0] = J.lut[trans_mask(2 * t, j0) & 0x3eu];
+            wO[1] = J.lut[trans_mask(2 * t + 1, j0 + 4) & 0x3eu];
+            const int c = t >> 7;        // one-step predecessors sit in slots s with (s & 3) == c   (warp-uniform)
+            const int sS = t >> 5;       // j >> 8: slot of the self predecessor                       (warp-uniform)
+            const int kT = t >> 1;       // low byte of the two-step predecessors
+            // column 0
+            {
+                const float4 e0 = *reinterpret_cast< const float4* >(E + j0);
+                const float4 e1 = *reinterpret_cast< const float4* >(E + j0 + 4);
+                float4 a0 = make_float4(__fsub_rn(e0.x, a.log_n_states), __fsub_rn(e0.y, a.log_n_states),
+                                        __fsub_rn(e0.z, a.log_n_states), __fsub_rn(e0.w, a.log_n_states));
+                float4 a1 = make_float4(__fsub_rn(e1.x, a.log_n_states), __fsub_rn(e1.y, a.log_n_states),
+                                        __fsub_rn(e1.z, a.log_n_states), __fsub_rn(e1.w, a.log_n_states));
+                *reinterpret_cast< float4* >(sm.col[0] + cphys(j0)) = a0;
+                *reinterpret_cast< float4* >(sm.col[0] + cphys(j0 + 4)) = a1;
+                *reinterpret_cast< float4* >(AL + j0) = a0;
+                *reinterpret_cast< float4* >(AL + j0 + 4) = a1;
+            }
+            __syncthreads();
+            int cur = 0;
+            for (unsigned i = 1; i < n; ++i)
+            {
+                const float* A = sm.col[cur];
+                float vT[16];
+#pragma unroll
+                for (int s = 0; s < 16; ++s) vT[s] = __fadd_rn(wT, A[cphys((s << 8) | (int)g)]);
+                float vO[2][4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                {
+                    const float2 o = *reinterpret_cast< const float2* >(A + cphys((b << 10) + 2 * t));
+                    vO[0][b] = __fadd_rn(wO[0], o.x);
+                    vO[1][b] = __fadd_rn(wO[1], o.y);
+                }
+                float own[FB_SPT];
+                {
+                    const float4 o0 = *reinterpret_cast< const float4* >(A + cphys(j0));
+                    const float4 o1 = *reinterpret_cast< const float4* >(A + cphys(j0 + 4));
+                    own[0] = o0.x; own[1] = o0.y; own[2] = o0.z; own[3] = o0.w;
+                    own[4] = o1.x; own[5] = o1.y; own[6] = o1.z; own[7] = o1.w;
+                }
+                float res[FB_SPT];
+#pragma unroll
+                for (int k = 0; k < FB_SPT; ++k)
+                {
+                    const int hh = k >> 2;
+                    const unsigned j = j0 + k;
+                    const int kO = (2 * t + hh) & 255;
+                    const int kS = j & 255;
+                    const bool oBefT = kO < kT, oEqT = kO == kT;
+                    const bool sEqT = kS == kT, sEqO = kS == kO;
+                    const float vS = __fadd_rn(J.lut[trans_mask(j, j)], own[k]);
+                    float acc = NC_NEG_INF;
+#pragma unroll
+                    for (int s = 0; s < 16; ++s)
+                    {
+                        const bool hasO = (s & 3) == c;
+                        const bool hasS = s == sS;
+                        if (!hasO && !hasS) acc = flogsum(acc, vT[s], tbl);
+                        else
+                        {
+                            const bool dropT = (hasO && oEqT) || (hasS && sEqT);
+                            const bool dropO = !hasO || (hasS && sEqO);
+                            const float xT = dropT ? NC_NEG_INF : vT[s];
+                            const float xO = dropO ? NC_NEG_INF : vO[hh][s >> 2];
+                            const bool oFirst = hasO && oBefT;
+                            const float first = oFirst ? xO : xT;
+                            const float second = oFirst ? xT : xO;
+                            if (!hasS)
+                            {
+                                acc = flogsum(acc, first, tbl);
+                                acc = flogsum(acc, second, tbl);
+                            }
+                            else
+                            {
+                                const int pos = (kT < kS ? 1 : 0) + ((hasO && kO < kS) ? 1 : 0);
+                                acc = flogsum(acc, pos == 0 ? vS : NC_NEG_INF, tbl);
+                                acc = flogsum(acc, first, tbl);
+                                acc = flogsum(acc, pos == 1 ? vS : NC_NEG_INF, tbl);
+                                acc = flogsum(acc, second, tbl);
+                                acc = flogsum(acc, pos == 2 ? vS : NC_NEG_INF, tbl);
+                            }
+                        }
+                    }
+                    res[k] = acc;
+                }
+                const float4 e0 = *reinterpret_cast< const float4* >(E + (size_t)i * NC_N_STATES + j0);
+                const float4 e1 = *reinterpret_cast< const float4* >(E + (size_t)i * NC_N_STATES + j0 + 4);
+                const float4 a0 = make_float4(__fadd_rn(e0.x, res[0]), __fadd_rn(e0.y, res[1]), __fadd_rn(e0.z, res[2]), __fadd_rn(e0.w, res[3]));
+                const float4 a1 = make_float4(__fadd_rn(e1.x, res[4]), __fadd_rn(e1.y, res[5]), __fadd_rn(e1.z, res[6]), __fadd_rn(e1.w, res[7]));
+                float* An = sm.col[cur ^ 1];
+                *reinterpret_cast< float4* >(An + cphys(j0)) = a0;
+                *reinterpret_cast< float4* >(An + cphys(j0 + 4)) = a1;
+                *reinterpret_cast< float4* >(AL + (size_t)i * NC_N_STATES + j0) = a0;
+                *reinterpret_cast< float4* >(AL + (size_t)i * NC_N_STATES + j0 + 4) = a1;
+                cur ^= 1;
+                __syncthreads();
+            }
+            // log Pr[data]: sequential fold of the last column, ascending j (Forward_Backward.hpp:129-134).
+            // One warp: each lane screens 32 values against the running sum -- a term with sum - x >= 15.999
+            // leaves p7_FLogsum's result unchanged now and for every larger sum -- and only the rest is folded.
+            if (t < 32)
+            {
+                const float* A = sm.col[cur];
+                float acc = NC_NEG_INF;
+                for (int base = 0; base < (int)NC_N_STATES; base += 32)
+                {
+                    const float x = A[cphys(base + lane)];
+                    unsigned live = __ballot_sync(0xffffffffu, !((x == NC_NEG_INF) || (acc > x && __fsub_rn(acc, x) >= 15.999f)));
+                    while (live)
+                    {
+                        const int b = __ffs(live) - 1;
+                        live &= live - 1;
+                        acc = flogsum(acc, __shfl_sync(0xffffffffu, x, b), tbl);
+                    }
+                }
+                if (lane == 0) a.log_pr_data[seq] = acc;
+            }
+            __syncthreads();
+        }
+
+        // =========================== backward (Forward_Backward.hpp:93-125); thread owns j = t + 512k
+        {
+            const int tb = (t & 255) << 4;                 // two-step successors tb .. tb+15 (same for all 8 states)
+            const float wTb = J.lut[trans_mask(t, tb) & 0x3cu];
+            float wOb[2];
+            int ob[2];
+            ob[0] = t << 2;                                // one-step successors of j with (j & 1023) == t
+            ob[1] = (t + 512) << 2;                        //                                      == t + 512
+            wOb[0] = J.lut[trans_mask(t, ob[0]) & 0x3eu];
+            wOb[1] = J.lut[trans_mask(t + 512, ob[1]) & 0x3eu];
+            // beta[n-1] = 0
+            {
+#pragma unroll
+                for (int k = 0; k < FB_SPT; ++k)
+                {
+                    const int j = t + FB_THREADS * k;
+                    sm.col[0][cphys(j)] = 0.0f;
+                    BE[(size_t)(n - 1) * NC_N_STATES + j] = 0.0f;
+                }
+            }
+            __syncthreads();
+            int cur = 0;
+            for (unsigned ip1 = n - 1; ip1 > 0; --ip1)
+            {
+                const unsigned i = ip1 - 1;
+                const float* Bn = sm.col[cur];
+                const float* En = E + (size_t)ip1 * NC_N_STATES;
+                float vT[16];
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                {
+                    const float4 e = __ldg(reinterpret_cast< const float4* >(En + tb) + v);
+                    const float4 b = *reinterpret_cast< const float4* >(Bn + cphys(tb) + 4 * v);
+                    vT[4 * v + 0] = __fadd_rn(__fadd_rn(wTb, e.x), b.x);
+                    vT[4 * v + 1] = __fadd_rn(__fadd_rn(wTb, e.y), b.y);
+                    vT[4 * v + 2] = __fadd_rn(__fadd_rn(wTb, e.z), b.z);
+                    vT[4 * v + 3] = __fadd_rn(__fadd_rn(wTb, e.w), b.w);
+                }
+                float res[FB_SPT];
+#pragma unroll
+                for (int f = 0; f < 2; ++f)
+                {
+                    float vO[4];
+                    {
+                        const float4 e = __ldg(reinterpret_cast< const float4* >(En + ob[f]));
+                        const float4 b = *reinterpret_cast< const float4* >(Bn + cphys(ob[f]));
+                        vO[0] = __fadd_rn(__fadd_rn(wOb[f], e.x), b.x);
+                        vO[1] = __fadd_rn(__fadd_rn(wOb[f], e.y), b.y);
+                        vO[2] = __fadd_rn(__fadd_rn(wOb[f], e.z), b.z);
+                        vO[3] = __fadd_rn(__fadd_rn(wOb[f], e.w), b.w);
+                    }
+                    // merged, ordered list of the 20 block successors of this family
+                    const bool oIn = (ob[f] >> 4) == (tb >> 4);
+                    const bool oBef = !oIn && ob[f] < tb;
+                    const int c4 = (ob[f] & 15) >> 2;
+                    float L[20];
+#pragma unroll
+                    for (int q = 0; q < 20; ++q)
+                    {
+                        // position q holds: oBef ? (q < 4 ? O[q] : T[q-4]) : (q < 16 ? T[q] : O[q-16])
+                        float asT, asO;
+                        if (q < 4) { asO = vO[q]; asT = vT[q]; }
+                        else if (q < 16) { asO = vT[q - 4]; asT = vT[q]; }
+                        else { asO = vT[q - 4]; asT = vO[q - 16]; }
+                        float val = oBef ? asO : asT;
+                        if (q < 16)
+                        {
+                            // oIn: the block is T with entries 4*c4 .. 4*c4+3 carrying the one-step weight
+                            const bool rep = oIn && ((q >> 2) == c4);
+                            val = rep ? vO[q & 3] : val;
+                        }
+                        else val = oIn ? NC_NEG_INF : val;
+                        L[q] = val;
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                    {
+                        const int k = 2 * kk + f;
+                        const int j = t + FB_THREADS * k;
+                        const float vS = __fadd_rn(__fadd_rn(J.lut[trans_mask(j, j)], __ldg(En + j)), Bn[cphys(j)]);
+                        const bool sInT = (j >> 4) == (tb >> 4);
+                        const bool sInO = (j >> 2) == (ob[f] >> 2);
+                        // position of j inside the list when it coincides with a block entry, else -1
+                        int mpos = -1;
+                        if (sInT) mpos = (oBef ? 4 : 0) + (j & 15);
+                        else if (sInO) mpos = (oBef ? 0 : 16) + (j & 3);
+                        // otherwise: number of blocks entirely below j
+                        const int pos = (mpos >= 0) ? -1 : ((j > tb ? 1 : 0) + ((!oIn && j > ob[f]) ? 1 : 0));
+                        float acc = NC_NEG_INF;
+                        acc = flogsum(acc, pos == 0 ? vS : NC_NEG_INF, tbl);
+#pragma unroll
+                        for (int q = 0; q < 20; ++q)
+                        {
+                            if (q == 4) acc = flogsum(acc, (oBef && pos == 1) ? vS : NC_NEG_INF, tbl);
+                            if (q == 16) acc = flogsum(acc, (!oBef && pos == 1) ? vS : NC_NEG_INF, tbl);
+                            acc = flogsum(acc, (q == mpos) ? vS : L[q], tbl);
+                        }
+                        acc = flogsum(acc, pos == 2 ? vS : NC_NEG_INF, tbl);
+                        res[k] = acc;
+                    }
+                }
+                float* Bc = sm.col[cur ^ 1];
+#pragma unroll
+                for (int k = 0; k < FB_SPT; ++k)
+                {
+                    const int j = t + FB_THREADS * k;
+                    Bc[cphys(j)] = res[k];
+                    BE[(size_t)i * NC_N_STATES + j] = res[k];
+                }
+                cur ^= 1;
+                __syncthreads();
+            }
+        }
+    }
 }
+
+size_t fwbw_smem_bytes() { return sizeof(FbSmem); }
+size_t st_stats_smem_bytes() { return sizeof(StSmem); }
+
+// ------------------------------------------------------------------------------------------------
+// train_pm_params' inner sums (Parameter_Trainer.hpp:263-296): per event
+//   s0 = sum_j p/sigma^2, s1 = sum_j p*mu/sigma^2, s2 = sum_j p*mu^2/sigma^2,
+//   l0 = sum_j p*lambda,  l1 = sum_j p*lambda/eta,  l2 = sum_j p*lambda/eta^2      (UNSCALED model)
+// with p = exp(alpha + beta - logZ).  The reference adds the 4096 terms sequentially in float; here each thread
+// adds its 8 consecutive states in order and a fixed-shape tree combines the 512 partials (deterministic; equal to
+// the reference to float rounding, ~1e-7 relative).
+__global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
+{
+    __shared__ float red[6][FB_THREADS / 32];
+    const unsigned seq = blockIdx.y;
+    const FbSeq& Q = a.seqs[seq];
+    const unsigned i0 = blockIdx.x * FB_EV_TILE;
+    if (i0 >= Q.n_events) return;
+    const unsigned n = Q.n_events;
+    const DevJob& J = a.jobs[Q.job];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned j0 = FB_SPT * t;
+    const float* M = a.models + (size_t)J.model * MODEL_FLOATS;
+    const float* AL = a.scratch + Q.slab + 1 * (size_t)n * NC_N_STATES;
+    const float* BE = a.scratch + Q.slab + 2 * (size_t)n * NC_N_STATES;
+    const float logz = a.log_pr_data[seq];
+    float mu[FB_SPT], isg2[FB_SPT], lam[FB_SPT], eta[FB_SPT];
+#pragma unroll
+    for (int k = 0; k < FB_SPT; ++k)
+    {
+        mu[k] = __ldg(M + 0 * NC_N_STATES + j0 + k);
+        const float sg = __ldg(M + 1 * NC_N_STATES + j0 + k);
+        isg2[k] = __fmul_rn(sg, sg);
+        eta[k] = __ldg(M + 2 * NC_N_STATES + j0 + k);
+        lam[k] = __ldg(M + 3 * NC_N_STATES + j0 + k);
+    }
+    const unsigned i1 = min(i0 + FB_EV_TILE, n);
+    for (unsigned i = i0; i < i1; ++i)
+    {
+        float s[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+#pragma unroll
+        for (int k = 0; k < FB_SPT; ++k)
+        {
+            const float lp = __fsub_rn(__fadd_rn(AL[(size_t)i * NC_N_STATES + j0 + k], BE[(size_t)i * NC_N_STATES + j0 + k]), logz);
+            const float p = expf(lp);
+            const float ts0 = __fdiv_rn(p, isg2[k]);
+            const float ts1 = __fmul_rn(ts0, mu[k]);
+            const float ts2 = __fmul_rn(ts1, mu[k]);
+            const float tl0 = __fmul_rn(p, lam[k]);
+            const float tl1 = __fdiv_rn(tl0, eta[k]);
+            const float tl2 = __fdiv_rn(tl1, eta[k]);
+            s[0] = __fadd_rn(s[0], ts0); s[1] = __fadd_rn(s[1], ts1); s[2] = __fadd_rn(s[2], ts2);
+            s[3] = __fadd_rn(s[3], tl0); s[4] = __fadd_rn(s[4], tl1); s[5] = __fadd_rn(s[5], tl2);
+        }
+#pragma unroll
+        for (int v = 0; v < 6; ++v)
+        {
+            float x = s[v];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                // combine neighbouring partials in ascending-state order: (lower half) + (upper half)
+                const float o = __shfl_xor_sync(0xffffffffu, x, d);
+                x = ((lane & d) == 0) ? __fadd_rn(x, o) : __fadd_rn(o, x);
+            }
+            if (lane == 0) red[v][warp] = x;
+        }
+        __syncthreads();
+        if (t < 6)
+        {
+            float x = red[t][0];
+            for (int w = 1; w < FB_THREADS / 32; ++w) x = __fadd_rn(x, red[t][w]);
+            a.pm_stats[(Q.ev_out + i) * 6 + t] = x;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// train_st_params' accumulators (Parameter_Trainer.hpp:434-517) for one (group, strand):
+//   denom (+)= post(i,j1);  stay (+)= min(joint(j1->j1 | log p_stay), post);
+//   skip (+)= log(exp(post) - exp(min(d01, post))),  d01 = stay' (+) the 4 one-step joints with log(p_step/4)
+// over the strand's sequences in order, events i < n-1, the 2160 training k-mers in ascending order.  The terms of
+// 512 k-mers at a time are computed in parallel, then three warps fold them sequentially (screening out terms that
+// cannot change the running sum, as in the logZ fold above).
+__global__ void __launch_bounds__(FB_THREADS) st_stats_kernel(const FbArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StSmem& ss = *reinterpret_cast< StSmem* >(smem_raw);
+    float* tbl = ss.tbl;
+    float (*term)[FB_THREADS] = ss.term;
+    float* accs = ss.accs;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int q = t; q < 16000; q += FB_THREADS) tbl[q] = a.logsum_tbl[q];
+    const unsigned grp = blockIdx.x;
+    const unsigned st = blockIdx.y;
+    const FbGroup& G = a.groups[grp];
+    if (t < 3) accs[t] = NC_NEG_INF;
+    __syncthreads();
+    for (unsigned sq = G.seq_begin; sq < G.seq_end; ++sq)
+    {
+        const FbSeq& Q = a.seqs[sq];
+        if (Q.strand != st) continue;
+        const unsigned n = Q.n_events;
+        const float* E = a.scratch + Q.slab;
+        const float* AL = a.scratch + Q.slab + 1 * (size_t)n * NC_N_STATES;
+        const float* BE = a.scratch + Q.slab + 2 * (size_t)n * NC_N_STATES;
+        const float logz = a.log_pr_data[sq];
+        const float log_p_stay = G.log_p_stay[st];
+        const float log_p_step_4 = G.log_p_step_4[st];
+        for (unsigned i = 0; i + 1 < n; ++i)
+        {
+            const float* Ai = AL + (size_t)i * NC_N_STATES;
+            const float* Bi = BE + (size_t)i * NC_N_STATES;
+            const float* Bn = BE + (size_t)(i + 1) * NC_N_STATES;
+            const float* En = E + (size_t)(i + 1) * NC_N_STATES;
+            for (unsigned base = 0; base < a.n_train_kmers; base += FB_THREADS)
+            {
+                float t_denom = NC_NEG_INF, t_stay = NC_NEG_INF, t_skip = NC_NEG_INF;
+                if (base + t < a.n_train_kmers)
+                {
+                    const unsigned j1 = a.train_kmers[base + t];
+                    const float al = Ai[j1];
+                    const float log_p_j1 = __fsub_rn(__fadd_rn(al, Bi[j1]), logz);
+                    // joint(i, j1, j2, lt) = alpha + lt + emission(j2, e_{i+1}) + beta(i+1, j2) - logZ   (:457-469)
+                    float jj = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_stay), En[j1]), Bn[j1]), logz);
+                    if (jj > log_p_j1) jj = log_p_j1;
+                    float s2 = flogsum(NC_NEG_INF, jj, tbl);
+                    const unsigned nb = (j1 & 1023u) << 2;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                    {
+                        const float jv = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_step_4), En[nb + b]), Bn[nb + b]), logz);
+                        s2 = flogsum(s2, jv, tbl);
+                    }
+                    if (s2 > log_p_j1) s2 = log_p_j1;
+                    const float p2 = __fsub_rn(expf(log_p_j1), expf(s2));
+                    t_denom = log_p_j1;
+                    t_stay = jj;
+                    t_skip = logf(p2);
+                }
+                term[0][t] = t_denom;
+                term[1][t] = t_stay;
+                term[2][t] = t_skip;
+                __syncthreads();
+                if (warp < 3)
+                {
+                    float acc = accs[warp];
+                    for (int b0 = 0; b0 < FB_THREADS; b0 += 32)
+                    {
+                        const float x = term[warp][b0 + lane];
+                        // NaN terms (log of a negative difference cannot occur: d01 <= post) are folded like the reference would
+                        unsigned live = __ballot_sync(0xffffffffu, !((x == NC_NEG_INF) || (acc > x && __fsub_rn(acc, x) >= 15.999f)));
+                        while (live)
+                        {
+                            const int b = __ffs(live) - 1;
+                            live &= live - 1;
+                            acc = flogsum(acc, __shfl_sync(0xffffffffu, x, b), tbl);
+                        }
+                    }
+                    if (lane == 0) accs[warp] = acc;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    if (t < 3) a.st_stats[(grp * 2 + st) * 3 + t] = accs[t];   // denom, stay, skip
+}
+
+} // namespace nc

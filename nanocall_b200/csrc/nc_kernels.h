@@ -32,6 +32,58 @@ struct VitArgs
 __global__ void viterbi_kernel(const VitArgs a);
 size_t viterbi_smem_bytes();
 
+// ---- Forward/Backward + trainer statistics
+enum { FB_EV_TILE = 16 };
+
+struct FbSeq
+{
+    unsigned long long ev_off;  // first event in the packed arrays
+    unsigned long long slab;    // float offset of this sequence's E | alpha | beta slab in the scratch pool
+    unsigned long long ev_out;  // first row of this sequence in pm_stats
+    unsigned n_events;
+    unsigned job;               // index into jobs: model + scaling + transition LUT of the sequence's strand
+    unsigned strand;
+    unsigned pad;
+};
+
+struct FbGroup
+{
+    unsigned seq_begin, seq_end;   // sequences of the group, in the caller's order
+    float log_p_stay[2];           // logf(p_stay)                          (Parameter_Trainer.hpp:443)
+    float log_p_step_4[2];         // (float)(log(1 - p_stay - p_skip) - log(4))   (:444)
+};
+
+struct FbArgs
+{
+    const DevJob* jobs;
+    const FbSeq* seqs;
+    const FbGroup* groups;
+    unsigned n_seqs;
+    unsigned n_groups;
+    unsigned* next_item;
+    const float* models;
+    const float* mean;
+    const float* stdv;
+    const float* start;
+    const float* log_stdv;
+    const float* logsum_tbl;       // 16000 floats (logsum.hpp:113-127)
+    const unsigned* train_kmers;   // Parameter_Trainer::st_train_kmers()
+    unsigned n_train_kmers;
+    float* scratch;
+    float* log_pr_data;            // n_seqs
+    float* pm_stats;               // total training events x 6
+    float* st_stats;               // n_groups x 2 strands x {denom, stay, skip}
+    float log_2pi;
+    float log_n_states;
+};
+
+__global__ void emission_kernel(const FbArgs a);
+__global__ void fwbw_kernel(const FbArgs a);
+__global__ void pm_stats_kernel(const FbArgs a);
+__global__ void st_stats_kernel(const FbArgs a);
+size_t fwbw_smem_bytes();
+size_t st_stats_smem_bytes();
+
 } // namespace nc
 
 #endif

@@ -1,0 +1,443 @@
+// Host side of K2: nc_fwbw (parity/debug entry) and nc_train_round_batch = one
+// Parameter_Trainer::train_one_round (Parameter_Trainer.hpp:541-579) for a batch of groups.
+// The device produces log Pr[data] per sequence, the six posterior sums per event and the three
+// transition accumulators per (group, strand); this file finishes the round on the host exactly as the
+// reference does: double accumulation over events in order, 3x3 Gaussian elimination with scaled partial
+// pivoting (:339-390), var / scale_sd / var_sd (:406-426), exp of the accumulator differences and clamps
+// (:516-530).
+#include "nc_ctx.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+// Parameter_Trainer::init (Parameter_Trainer.hpp:30-57): k-mers without self-overlap whose one-step
+// neighbours have self-overlap <= 1.  max_self_overlap as Kmer.hpp:81-110.
+unsigned max_self_overlap(unsigned i)
+{
+    for (unsigned k = NC_KMER - 1; k >= 1; --k)
+        if ((i & ((1u << (2 * k)) - 1)) == (i >> (2 * (NC_KMER - k)))) return k;
+    return 0;
+}
+
+int ensure_train_tables(nc_ctx* ctx)
+{
+    if (ctx->d_logsum_tbl && ctx->d_train_kmers) return NC_OK;
+    NC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->d_logsum_tbl)
+    {
+        // p7_FLogsumInit (logsum.hpp:113-127): double log/exp, stored as float
+        std::vector< float > tbl(16000);
+        for (int i = 0; i < 16000; ++i) tbl[i] = (float)std::log(1. + std::exp((double)-i / 1000.f));
+        NC_CUDA(ctx, cudaMalloc(&ctx->d_logsum_tbl, tbl.size() * sizeof(float)));
+        NC_CUDA(ctx, cudaMemcpy(ctx->d_logsum_tbl, tbl.data(), tbl.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (!ctx->d_train_kmers)
+    {
+        std::vector< unsigned > km;
+        for (unsigned i = 0; i < NC_N_STATES; ++i)
+        {
+            if (max_self_overlap(i) > 0) continue;
+            bool all_good = true;
+            for (unsigned b1 = 0; b1 < 4; ++b1)
+            {
+                unsigned j = ((i & 1023u) << 2) + b1;
+                if (max_self_overlap(j) > 1) { all_good = false; break; }
+            }
+            if (all_good) km.push_back(i);
+        }
+        NC_CUDA(ctx, cudaMalloc(&ctx->d_train_kmers, km.size() * sizeof(unsigned)));
+        NC_CUDA(ctx, cudaMemcpy(ctx->d_train_kmers, km.data(), km.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+        ctx->n_train_kmers = (unsigned)km.size();
+    }
+    NC_CUDA(ctx, cudaFuncSetAttribute(nc::fwbw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nc::fwbw_smem_bytes()));
+    NC_CUDA(ctx, cudaFuncSetAttribute(nc::st_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nc::st_stats_smem_bytes()));
+    return NC_OK;
+}
+
+void fill_job(nc::DevJob& J, int model, const nc_pm_params& pm, const nc_st_params& st)
+{
+    J.ev_off = 0;
+    J.n_events = 0;
+    J.model = model;
+    J.scale = pm.scale; J.shift = pm.shift; J.drift = pm.drift;
+    J.var = pm.var; J.scale_sd = pm.scale_sd; J.var_sd = pm.var_sd;
+    nc::host_job_logs(pm, J.log_var, J.log_var_sd);
+    nc_transition_lut(st.p_stay, st.p_skip, J.lut);
+}
+
+size_t scratch_limit(nc_ctx* ctx)
+{
+    if (ctx->fb_scratch_limit) return ctx->fb_scratch_limit;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (size_t)1 << 30;
+    size_t have = ctx->fb_scratch.cap;
+    return std::min< size_t >((free_b + have) / 2, (size_t)24 << 30);
+}
+
+// train_pm_params after the inner sums (Parameter_Trainer.hpp:297-427).  rows: per event {s0,s1,s2,l0,l1,l2};
+// x/y/t: uncorrected mean, stdv (after the 0 -> 0.01 fix) and start of the same events, in (sequence, event) order.
+void finish_pm(size_t n_ev, const float* rows, const float* x, const float* y, const float* t, bool train_drift,
+               const nc_pm_params& crt, nc_pm_params& out, int& done)
+{
+    done = 0;
+    double A[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+    double B[3] = { 0, 0, 0 };
+    double D = 0.0, V_numer = 0.0, V_denom = 0.0, U_pos = 0.0;
+    for (size_t i = 0; i < n_ev; ++i)
+    {
+        const float* s = rows + 6 * i;
+        const float* l = s + 3;
+        float x_i = x[i], y_i = y[i], t_i = t[i];
+        A[0][0] += s[0];
+        A[0][1] += s[1];
+        A[1][1] += s[2];
+        B[0] += s[0] * x_i;
+        B[1] += s[1] * x_i;
+        if (train_drift)
+        {
+            A[0][2] += s[0] * t_i;
+            A[1][2] += s[1] * t_i;
+            A[2][2] += s[0] * t_i * t_i;
+            B[2] += s[0] * x_i * t_i;
+        }
+        D += s[0] * x_i * x_i;
+        V_numer += l[2] * y_i;
+        V_denom += l[1];
+        U_pos += l[0] / y_i;
+    }
+    A[1][0] = A[0][1];
+    A[2][0] = A[0][2];
+    A[2][1] = A[1][2];
+    if (!train_drift) A[2][2] = 1.0;
+    double Ac[3][3], Bc[3], C[3];
+    std::memcpy(Ac, A, sizeof A);
+    std::memcpy(Bc, B, sizeof B);
+    for (unsigned i = 0; i < 3; ++i)
+    {
+        C[i] = A[i][0];
+        for (unsigned j = 1; j < 3; ++j) if (C[i] < A[i][j]) C[i] = A[i][j];
+    }
+    for (unsigned i = 0; i < 3; ++i)
+    {
+        unsigned p = i;
+        double p_val = std::abs(A[i][i]) / C[p];
+        for (unsigned i2 = i + 1; i2 < 3; ++i2)
+        {
+            double i2_val = std::abs(A[i2][i]) / C[i2];
+            if (i2_val > p_val) { p = i2; p_val = i2_val; }
+        }
+        if (p_val < 1e-7)
+        {
+            done = 1;
+            out = crt;
+            return;
+        }
+        if (p > i)
+        {
+            for (unsigned j = 0; j < 3; ++j) std::swap(A[i][j], A[p][j]);
+            std::swap(B[i], B[p]);
+            std::swap(C[i], C[p]);
+        }
+        for (p = i + 1; p < 3; ++p)
+        {
+            double m = A[p][i] / A[i][i];
+            A[p][i] = 0;
+            for (unsigned j = i + 1; j < 3; ++j) A[p][j] -= m * A[i][j];
+            B[p] -= m * B[i];
+        }
+    }
+    // the solution is stored into float members as it is produced (:236-241,406-426)
+    float c_hat = (float)(B[2] / A[2][2]);
+    float b_hat = (float)((B[1] - A[1][2] * c_hat) / A[1][1]);
+    float a_hat = (float)((B[0] - A[0][1] * b_hat - A[0][2] * c_hat) / A[0][0]);
+    double d_numer = (D
+                      + a_hat * a_hat * Ac[0][0]
+                      + b_hat * b_hat * Ac[1][1]
+                      + c_hat * c_hat * Ac[2][2]
+                      + 2.0 * a_hat * b_hat * Ac[0][1]
+                      + 2.0 * a_hat * c_hat * Ac[0][2]
+                      + 2.0 * b_hat * c_hat * Ac[1][2]
+                      - 2.0 * (a_hat * Bc[0] + b_hat * Bc[1] + c_hat * Bc[2]));
+    float d_hat = (float)std::sqrt(d_numer / (double)n_ev);
+    float v_hat = (float)(V_numer / V_denom);
+    float u_hat = (float)((double)n_ev / (U_pos - V_denom / v_hat));
+    out.shift = a_hat; out.scale = b_hat; out.drift = c_hat; out.var = d_hat; out.scale_sd = v_hat; out.var_sd = u_hat;
+}
+
+// Parameter_Trainer.hpp:516-530
+nc_st_params finish_st(const float* acc /* denom, stay, skip */)
+{
+    nc_st_params r;
+    r.p_stay = std::exp(acc[1] - acc[0]);
+    r.p_skip = std::exp(acc[2] - acc[0]);
+    if (r.p_stay < .05 || r.p_stay > .4 || r.p_skip < .05 || r.p_skip > .4)
+    {
+        float a_stay = std::max(r.p_stay, .05f);
+        a_stay = std::min(a_stay, .4f);
+        float a_skip = std::max(r.p_skip, .05f);
+        a_skip = std::min(a_skip, .4f);
+        r.p_stay = a_stay;
+        r.p_skip = a_skip;
+    }
+    return r;
+}
+
+struct Wave
+{
+    std::vector< nc::FbSeq > seqs;
+    std::vector< nc::FbGroup > groups;
+    std::vector< nc::DevJob > jobs;
+    size_t scratch_floats = 0;
+    size_t n_events = 0;
+    unsigned max_len = 0;
+};
+
+// Upload a wave's descriptors and run emission + fwbw (+ stats).  Event arrays are already on the device.
+int run_wave(nc_ctx* ctx, const Wave& w, const float* d_mean, const float* d_stdv, const float* d_start, const float* d_lstd,
+             bool pm_stats, bool st_stats, std::vector< float >& lz, std::vector< float >& pm_rows, std::vector< float >& st_acc)
+{
+    int rc;
+    const unsigned ns = (unsigned)w.seqs.size(), ng = (unsigned)w.groups.size();
+    if ((rc = dev_reserve(ctx, ctx->fb_scratch, w.scratch_floats * sizeof(float))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_seqs, ns * sizeof(nc::FbSeq))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_groups, std::max(1u, ng) * sizeof(nc::FbGroup))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_jobs, w.jobs.size() * sizeof(nc::DevJob))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_lz, ns * sizeof(float))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_pm, std::max< size_t >(1, w.n_events) * 6 * sizeof(float))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_st, std::max(1u, ng) * 6 * sizeof(float))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_counter, sizeof(unsigned))) != NC_OK) return rc;
+    cudaStream_t s = ctx->stream;
+    NC_CUDA(ctx, cudaMemcpyAsync(ctx->fb_seqs.p, w.seqs.data(), ns * sizeof(nc::FbSeq), cudaMemcpyHostToDevice, s));
+    if (ng) NC_CUDA(ctx, cudaMemcpyAsync(ctx->fb_groups.p, w.groups.data(), ng * sizeof(nc::FbGroup), cudaMemcpyHostToDevice, s));
+    NC_CUDA(ctx, cudaMemcpyAsync(ctx->fb_jobs.p, w.jobs.data(), w.jobs.size() * sizeof(nc::DevJob), cudaMemcpyHostToDevice, s));
+    NC_CUDA(ctx, cudaMemsetAsync(ctx->fb_counter.p, 0, sizeof(unsigned), s));
+
+    nc::FbArgs a;
+    a.jobs = (const nc::DevJob*)ctx->fb_jobs.p;
+    a.seqs = (const nc::FbSeq*)ctx->fb_seqs.p;
+    a.groups = (const nc::FbGroup*)ctx->fb_groups.p;
+    a.n_seqs = ns;
+    a.n_groups = ng;
+    a.next_item = (unsigned*)ctx->fb_counter.p;
+    a.models = ctx->d_models;
+    a.mean = d_mean; a.stdv = d_stdv; a.start = d_start; a.log_stdv = d_lstd;
+    a.logsum_tbl = ctx->d_logsum_tbl;
+    a.train_kmers = ctx->d_train_kmers;
+    a.n_train_kmers = ctx->n_train_kmers;
+    a.scratch = (float*)ctx->fb_scratch.p;
+    a.log_pr_data = (float*)ctx->fb_lz.p;
+    a.pm_stats = (float*)ctx->fb_pm.p;
+    a.st_stats = (float*)ctx->fb_st.p;
+    a.log_2pi = (float)std::log(2.0 * M_PI);
+    a.log_n_states = std::log((float)NC_N_STATES);
+
+    const unsigned tiles = (w.max_len + nc::FB_EV_TILE - 1) / nc::FB_EV_TILE;
+    NC_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    nc::emission_kernel<<< dim3(tiles, ns), 512, 0, s >>>(a);
+    NC_CUDA(ctx, cudaGetLastError());
+    const unsigned grid = std::min< unsigned >(ns, 2u * (unsigned)ctx->prop.multiProcessorCount);
+    nc::fwbw_kernel<<< grid, 512, nc::fwbw_smem_bytes(), s >>>(a);
+    NC_CUDA(ctx, cudaGetLastError());
+    if (pm_stats)
+    {
+        nc::pm_stats_kernel<<< dim3(tiles, ns), 512, 0, s >>>(a);
+        NC_CUDA(ctx, cudaGetLastError());
+    }
+    if (st_stats && ng)
+    {
+        nc::st_stats_kernel<<< dim3(ng, 2), 512, nc::st_stats_smem_bytes(), s >>>(a);
+        NC_CUDA(ctx, cudaGetLastError());
+    }
+    NC_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    lz.resize(ns);
+    NC_CUDA(ctx, cudaMemcpyAsync(lz.data(), ctx->fb_lz.p, ns * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (pm_stats)
+    {
+        pm_rows.resize(w.n_events * 6);
+        NC_CUDA(ctx, cudaMemcpyAsync(pm_rows.data(), ctx->fb_pm.p, pm_rows.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    if (st_stats && ng)
+    {
+        st_acc.resize((size_t)ng * 6);
+        NC_CUDA(ctx, cudaMemcpyAsync(st_acc.data(), ctx->fb_st.p, st_acc.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    NC_CUDA(ctx, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    NC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_kernel_ms = ms;
+    return NC_OK;
+}
+
+int upload_events(nc_ctx* ctx, size_t total, const float* mean, const float* stdv, const float* start,
+                  std::vector< float >& y_fixed)
+{
+    int rc;
+    std::vector< float > lstd(total);
+    nc::host_event_logs(total, stdv, lstd.data(), ctx->host_threads);
+    y_fixed.resize(total);
+    for (size_t i = 0; i < total; ++i) y_fixed[i] = (stdv[i] == 0.0f) ? 0.01f : stdv[i];
+    if ((rc = dev_reserve(ctx, ctx->fb_mean, total * sizeof(float))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_stdv, total * sizeof(float))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_start, total * sizeof(float))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_lstd, total * sizeof(float))) != NC_OK) return rc;
+    NC_CUDA(ctx, cudaMemcpy(ctx->fb_mean.p, mean, total * sizeof(float), cudaMemcpyHostToDevice));
+    NC_CUDA(ctx, cudaMemcpy(ctx->fb_stdv.p, stdv, total * sizeof(float), cudaMemcpyHostToDevice));
+    NC_CUDA(ctx, cudaMemcpy(ctx->fb_start.p, start, total * sizeof(float), cudaMemcpyHostToDevice));
+    NC_CUDA(ctx, cudaMemcpy(ctx->fb_lstd.p, lstd.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    return NC_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int nc_fwbw(nc_ctx* ctx, int32_t model_id, const nc_pm_params* pm, const nc_st_params* st,
+            uint32_t n_events, const float* mean, const float* stdv, const float* start,
+            float* alpha, float* beta, float* log_pr_data)
+{
+    if (!ctx) return NC_ERR_ARG;
+    if (!pm || !st || !mean || !stdv || !start || n_events == 0) NC_FAIL(ctx, NC_ERR_ARG, "nc_fwbw: bad argument");
+    if (model_id < 0 || model_id >= (int)ctx->models.size()) NC_FAIL(ctx, NC_ERR_ARG, "nc_fwbw: unknown model id %d", model_id);
+    int rc;
+    if ((rc = ensure_train_tables(ctx)) != NC_OK) return rc;
+    std::vector< float > yfix;
+    if ((rc = upload_events(ctx, n_events, mean, stdv, start, yfix)) != NC_OK) return rc;
+    Wave w;
+    w.jobs.resize(1);
+    fill_job(w.jobs[0], model_id, *pm, *st);
+    nc::FbSeq q;
+    std::memset(&q, 0, sizeof q);
+    q.n_events = n_events;
+    w.seqs.push_back(q);
+    w.scratch_floats = (size_t)3 * n_events * NC_N_STATES;
+    w.n_events = n_events;
+    w.max_len = n_events;
+    std::vector< float > lz, pmr, sta;
+    if ((rc = run_wave(ctx, w, (const float*)ctx->fb_mean.p, (const float*)ctx->fb_stdv.p, (const float*)ctx->fb_start.p,
+                       (const float*)ctx->fb_lstd.p, false, false, lz, pmr, sta)) != NC_OK)
+        return rc;
+    const size_t cells = (size_t)n_events * NC_N_STATES;
+    const float* sc = (const float*)ctx->fb_scratch.p;
+    if (alpha) NC_CUDA(ctx, cudaMemcpy(alpha, sc + cells, cells * sizeof(float), cudaMemcpyDeviceToHost));
+    if (beta) NC_CUDA(ctx, cudaMemcpy(beta, sc + 2 * cells, cells * sizeof(float), cudaMemcpyDeviceToHost));
+    if (log_pr_data) *log_pr_data = lz[0];
+    return NC_OK;
+}
+
+int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off,
+                         const uint64_t* ev_off, const uint8_t* seq_strand,
+                         const float* mean, const float* stdv, const float* start,
+                         const nc_train_in* in, const nc_train_opts* opts, nc_train_out* out)
+{
+    if (!ctx) return NC_ERR_ARG;
+    if (n_groups == 0) return NC_OK;
+    if (!seq_off || !ev_off || !seq_strand || !mean || !stdv || !start || !in || !opts || !out)
+        NC_FAIL(ctx, NC_ERR_ARG, "nc_train_round_batch: NULL argument");
+    int rc;
+    if ((rc = ensure_train_tables(ctx)) != NC_OK) return rc;
+    const uint32_t n_seqs = seq_off[n_groups];
+    for (uint32_t g = 0; g < n_groups; ++g)
+    {
+        if (seq_off[g + 1] <= seq_off[g] || seq_off[g + 1] - seq_off[g] > NC_MAX_TRAIN_SEQS)
+            NC_FAIL(ctx, NC_ERR_ARG, "nc_train_round_batch: group %u has %u sequences (1..%u allowed)", g,
+                    seq_off[g + 1] - seq_off[g], NC_MAX_TRAIN_SEQS);
+        for (int st = 0; st < 2; ++st)
+            if (in[g].model_id[st] < 0 || in[g].model_id[st] >= (int)ctx->models.size())
+                NC_FAIL(ctx, NC_ERR_ARG, "nc_train_round_batch: group %u: unknown model id %d", g, in[g].model_id[st]);
+    }
+    for (uint32_t s = 0; s < n_seqs; ++s)
+    {
+        if (ev_off[s + 1] <= ev_off[s]) NC_FAIL(ctx, NC_ERR_ARG, "nc_train_round_batch: sequence %u has no events", s);
+        if (seq_strand[s] > 1) NC_FAIL(ctx, NC_ERR_ARG, "nc_train_round_batch: sequence %u: strand must be 0 or 1", s);
+    }
+    const uint64_t base = ev_off[0];
+    const size_t total = ev_off[n_seqs] - base;
+    std::vector< float > yfix;
+    if ((rc = upload_events(ctx, total, mean + base, stdv + base, start + base, yfix)) != NC_OK) return rc;
+    const size_t limit_floats = scratch_limit(ctx) / sizeof(float);
+
+    uint32_t g0 = 0;
+    std::vector< float > lz, pm_rows, st_acc;
+    while (g0 < n_groups)
+    {
+        // ---- a wave: consecutive groups whose slabs fit the scratch pool
+        Wave w;
+        uint32_t g1 = g0;
+        while (g1 < n_groups)
+        {
+            size_t need = 0;
+            for (uint32_t s = seq_off[g1]; s < seq_off[g1 + 1]; ++s) need += (size_t)3 * (ev_off[s + 1] - ev_off[s]) * NC_N_STATES;
+            if (g1 > g0 && (w.scratch_floats + need > limit_floats || w.seqs.size() + NC_MAX_TRAIN_SEQS > 60000)) break;
+            nc::FbGroup G;
+            G.seq_begin = (unsigned)w.seqs.size();
+            for (int st = 0; st < 2; ++st)
+            {
+                // Parameter_Trainer.hpp:443-444
+                G.log_p_stay[st] = std::log(in[g1].st[st].p_stay);
+                G.log_p_step_4[st] = (float)(std::log(1.0 - in[g1].st[st].p_stay - in[g1].st[st].p_skip) - std::log(4.0));
+                nc::DevJob J;
+                fill_job(J, in[g1].model_id[st], in[g1].pm, in[g1].st[st]);
+                w.jobs.push_back(J);
+            }
+            for (uint32_t s = seq_off[g1]; s < seq_off[g1 + 1]; ++s)
+            {
+                nc::FbSeq q;
+                std::memset(&q, 0, sizeof q);
+                q.ev_off = ev_off[s] - base;
+                q.n_events = (unsigned)(ev_off[s + 1] - ev_off[s]);
+                q.slab = w.scratch_floats;
+                q.ev_out = w.n_events;
+                q.job = 2 * (g1 - g0) + seq_strand[s];
+                q.strand = seq_strand[s];
+                w.scratch_floats += (size_t)3 * q.n_events * NC_N_STATES;
+                w.n_events += q.n_events;
+                w.max_len = std::max(w.max_len, q.n_events);
+                w.seqs.push_back(q);
+            }
+            G.seq_end = (unsigned)w.seqs.size();
+            w.groups.push_back(G);
+            ++g1;
+        }
+        if ((rc = run_wave(ctx, w, (const float*)ctx->fb_mean.p, (const float*)ctx->fb_stdv.p, (const float*)ctx->fb_start.p,
+                           (const float*)ctx->fb_lstd.p, opts->train_scaling != 0, opts->train_transitions != 0,
+                           lz, pm_rows, st_acc)) != NC_OK)
+            return rc;
+        // ---- finish every group of the wave on the host (train_one_round, :541-579)
+        for (uint32_t g = g0; g < g1; ++g)
+        {
+            const nc::FbGroup& G = w.groups[g - g0];
+            nc_train_out& o = out[g];
+            float fit = 0.0f;
+            for (unsigned q = G.seq_begin; q < G.seq_end; ++q) fit += lz[q];
+            o.fit = fit;
+            o.pm = in[g].pm;
+            o.st[0] = in[g].st[0];
+            o.st[1] = in[g].st[1];
+            o.done = 0;
+            if (opts->train_scaling)
+            {
+                const nc::FbSeq& first = w.seqs[G.seq_begin];
+                size_t n_ev = 0;
+                for (unsigned q = G.seq_begin; q < G.seq_end; ++q) n_ev += w.seqs[q].n_events;
+                // the group's events are contiguous in (sequence, event) order both in pm_rows and in the inputs
+                int done = 0;
+                finish_pm(n_ev, pm_rows.data() + 6 * first.ev_out, mean + base + first.ev_off, yfix.data() + first.ev_off,
+                          start + base + first.ev_off, opts->train_drift != 0, in[g].pm, o.pm, done);
+                o.done = done;
+                if (done) continue;  // new_st_params = crt_st_params (:566-570)
+            }
+            if (opts->train_transitions)
+            {
+                o.st[0] = finish_st(st_acc.data() + (size_t)(g - g0) * 6);
+                o.st[1] = finish_st(st_acc.data() + (size_t)(g - g0) * 6 + 3);
+            }
+        }
+        g0 = g1;
+    }
+    return NC_OK;
+}
+
+} // extern "C"
