@@ -94,6 +94,70 @@ __device__ __forceinline__ unsigned min_skip(unsigned k1, unsigned k2)
     return 6;
 }
 
+
+// expf with the bits of glibc's expf (sysdeps/ieee754/flt-32/e_expf.c, the ARM optimized-routines algorithm):
+// double arithmetic, N = 32 table of 2^(i/N), cubic polynomial.  The table is 2^(i/32) correctly rounded to
+// double minus (i << 47), regenerated from its definition (tools/gen_exp2f_table.py).  A C twin of this routine
+// agrees with libm's expf on every one of 23e6 sampled inputs (tools/check_expf.c); the trainer's posteriors
+// p = exp(alpha + beta - logZ) therefore carry the reference's bits (Parameter_Trainer.hpp:278).
+__device__ const unsigned long long nc_exp2f_tab[32] = {
+0x3ff0000000000000ULL,
+0x3fefd9b0d3158574ULL,
+0x3fefb5586cf9890fULL,
+0x3fef9301d0125b51ULL,
+0x3fef72b83c7d517bULL,
+0x3fef54873168b9aaULL,
+0x3fef387a6e756238ULL,
+0x3fef1e9df51fdee1ULL,
+0x3fef06fe0a31b715ULL,
+0x3feef1a7373aa9cbULL,
+0x3feedea64c123422ULL,
+0x3feece086061892dULL,
+0x3feebfdad5362a27ULL,
+0x3feeb42b569d4f82ULL,
+0x3feeab07dd485429ULL,
+0x3feea47eb03a5585ULL,
+0x3feea09e667f3bcdULL,
+0x3fee9f75e8ec5f74ULL,
+0x3feea11473eb0187ULL,
+0x3feea589994cce13ULL,
+0x3feeace5422aa0dbULL,
+0x3feeb737b0cdc5e5ULL,
+0x3feec49182a3f090ULL,
+0x3feed503b23e255dULL,
+0x3feee89f995ad3adULL,
+0x3feeff76f2fb5e47ULL,
+0x3fef199bdd85529cULL,
+0x3fef3720dcef9069ULL,
+0x3fef5818dcfba487ULL,
+0x3fef7c97337b9b5fULL,
+0x3fefa4afa2a490daULL,
+0x3fefd0765b6e4540ULL
+};
+
+__device__ __forceinline__ float nc_expf(float x)
+{
+    if (!(x > -0x1.9fe368p6f)) return (x != x) ? x : 0.0f;  // underflow (and -inf) -> 0
+    if (x > 0x1.62e42ep6f) return __int_as_float(0x7f800000);
+    const double InvLn2N = 0x1.71547652b82fep+0 * 32;
+    const double SHIFT = 0x1.8p+52;
+    const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32, C2 = 0x1.62e42ff0c52d6p-1 / 32;
+    double z = __dmul_rn(InvLn2N, (double)x);
+    double kd = __dadd_rn(z, SHIFT);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dsub_rn(kd, SHIFT);
+    const double r = __dsub_rn(z, kd);
+    unsigned long long t = __ldg(nc_exp2f_tab + (ki & 31u));
+    t += ki << 47;
+    const double s = __longlong_as_double((long long)t);
+    z = __dadd_rn(__dmul_rn(C0, r), C1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(C2, r), 1.0);
+    y = __dadd_rn(__dmul_rn(z, r2), y);
+    y = __dmul_rn(y, s);
+    return (float)y;
+}
+
 // Backpointer byte -> predecessor state.  0..15: two-step predecessor (bb<<8)|(j>>4);
 // 16..19: one-step predecessor (b<<10)|(j>>2); 20: j itself.
 __device__ __forceinline__ unsigned bp_decode(unsigned code, unsigned j)

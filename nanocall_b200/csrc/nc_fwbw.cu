@@ -388,12 +388,15 @@ size_t st_stats_smem_bytes() { return sizeof(StSmem); }
 // train_pm_params' inner sums (Parameter_Trainer.hpp:263-296): per event
 //   s0 = sum_j p/sigma^2, s1 = sum_j p*mu/sigma^2, s2 = sum_j p*mu^2/sigma^2,
 //   l0 = sum_j p*lambda,  l1 = sum_j p*lambda/eta,  l2 = sum_j p*lambda/eta^2      (UNSCALED model)
-// with p = exp(alpha + beta - logZ).  The reference adds the 4096 terms sequentially in float; here each thread
-// adds its 8 consecutive states in order and a fixed-shape tree combines the 512 partials (deterministic; equal to
-// the reference to float rounding, ~1e-7 relative).
+// with p = exp(alpha + beta - logZ).  The 3x3 system built from these sums is ill-conditioned (level means are
+// 58 +- 6 pA), so the float rounding of the reference's SEQUENTIAL j = 0..4095 accumulation is visible in the trained
+// shift/scale/var at the 1e-4 level: the order is reproduced exactly.  All terms are >= 0, so the running sum never
+// decreases and a term below half an ulp of it (t < acc * 2^-25) can never change it; one warp per sum screens 32
+// terms at a time against the running sum and adds only the rest, in order -- the same float result as the serial loop.
 __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
 {
-    __shared__ float red[6][FB_THREADS / 32];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float (*term)[NC_N_STATES] = reinterpret_cast< float (*)[NC_N_STATES] >(smem_raw);  // [6][4096]
     const unsigned seq = blockIdx.y;
     const FbSeq& Q = a.seqs[seq];
     const unsigned i0 = blockIdx.x * FB_EV_TILE;
@@ -406,57 +409,71 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
     const float* AL = a.scratch + Q.slab + 1 * (size_t)n * NC_N_STATES;
     const float* BE = a.scratch + Q.slab + 2 * (size_t)n * NC_N_STATES;
     const float logz = a.log_pr_data[seq];
-    float mu[FB_SPT], isg2[FB_SPT], lam[FB_SPT], eta[FB_SPT];
+    float mu[FB_SPT], sg2[FB_SPT], lam[FB_SPT], eta[FB_SPT];
 #pragma unroll
     for (int k = 0; k < FB_SPT; ++k)
     {
         mu[k] = __ldg(M + 0 * NC_N_STATES + j0 + k);
         const float sg = __ldg(M + 1 * NC_N_STATES + j0 + k);
-        isg2[k] = __fmul_rn(sg, sg);
+        sg2[k] = __fmul_rn(sg, sg);
         eta[k] = __ldg(M + 2 * NC_N_STATES + j0 + k);
         lam[k] = __ldg(M + 3 * NC_N_STATES + j0 + k);
     }
     const unsigned i1 = min(i0 + FB_EV_TILE, n);
     for (unsigned i = i0; i < i1; ++i)
     {
-        float s[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+        float al[FB_SPT], be[FB_SPT];
+        *reinterpret_cast< float4* >(al) = *reinterpret_cast< const float4* >(AL + (size_t)i * NC_N_STATES + j0);
+        *reinterpret_cast< float4* >(al + 4) = *reinterpret_cast< const float4* >(AL + (size_t)i * NC_N_STATES + j0 + 4);
+        *reinterpret_cast< float4* >(be) = *reinterpret_cast< const float4* >(BE + (size_t)i * NC_N_STATES + j0);
+        *reinterpret_cast< float4* >(be + 4) = *reinterpret_cast< const float4* >(BE + (size_t)i * NC_N_STATES + j0 + 4);
 #pragma unroll
         for (int k = 0; k < FB_SPT; ++k)
         {
-            const float lp = __fsub_rn(__fadd_rn(AL[(size_t)i * NC_N_STATES + j0 + k], BE[(size_t)i * NC_N_STATES + j0 + k]), logz);
-            const float p = expf(lp);
-            const float ts0 = __fdiv_rn(p, isg2[k]);
+            const float p = nc_expf(__fsub_rn(__fadd_rn(al[k], be[k]), logz));
+            const float ts0 = __fdiv_rn(p, sg2[k]);
             const float ts1 = __fmul_rn(ts0, mu[k]);
-            const float ts2 = __fmul_rn(ts1, mu[k]);
             const float tl0 = __fmul_rn(p, lam[k]);
             const float tl1 = __fdiv_rn(tl0, eta[k]);
-            const float tl2 = __fdiv_rn(tl1, eta[k]);
-            s[0] = __fadd_rn(s[0], ts0); s[1] = __fadd_rn(s[1], ts1); s[2] = __fadd_rn(s[2], ts2);
-            s[3] = __fadd_rn(s[3], tl0); s[4] = __fadd_rn(s[4], tl1); s[5] = __fadd_rn(s[5], tl2);
-        }
-#pragma unroll
-        for (int v = 0; v < 6; ++v)
-        {
-            float x = s[v];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1)
-            {
-                // combine neighbouring partials in ascending-state order: (lower half) + (upper half)
-                const float o = __shfl_xor_sync(0xffffffffu, x, d);
-                x = ((lane & d) == 0) ? __fadd_rn(x, o) : __fadd_rn(o, x);
-            }
-            if (lane == 0) red[v][warp] = x;
+            term[0][j0 + k] = ts0;
+            term[1][j0 + k] = ts1;
+            term[2][j0 + k] = __fmul_rn(ts1, mu[k]);
+            term[3][j0 + k] = tl0;
+            term[4][j0 + k] = tl1;
+            term[5][j0 + k] = __fdiv_rn(tl1, eta[k]);
         }
         __syncthreads();
-        if (t < 6)
+        if (warp < 6)
         {
-            float x = red[t][0];
-            for (int w = 1; w < FB_THREADS / 32; ++w) x = __fadd_rn(x, red[t][w]);
-            a.pm_stats[(Q.ev_out + i) * 6 + t] = x;
+            const float* T = term[warp];
+            float acc = 0.0f;
+            for (int base = 0; base < (int)NC_N_STATES; base += 64)
+            {
+                const float x0 = T[base + lane];
+                const float x1 = T[base + 32 + lane];
+                const float thr = __fmul_rn(acc, 2.98023223876953125e-8f);  // 2^-25
+                unsigned live0 = __ballot_sync(0xffffffffu, !(x0 < thr));
+                unsigned live1 = __ballot_sync(0xffffffffu, !(x1 < thr));
+                while (live0)
+                {
+                    const int b = __ffs(live0) - 1;
+                    live0 &= live0 - 1;
+                    acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x0, b));
+                }
+                while (live1)
+                {
+                    const int b = __ffs(live1) - 1;
+                    live1 &= live1 - 1;
+                    acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x1, b));
+                }
+            }
+            if (lane == 0) a.pm_stats[(Q.ev_out + i) * 6 + warp] = acc;
         }
         __syncthreads();
     }
 }
+
+size_t pm_stats_smem_bytes() { return 6 * NC_N_STATES * sizeof(float); }
 
 // ------------------------------------------------------------------------------------------------
 // train_st_params' accumulators (Parameter_Trainer.hpp:434-517) for one (group, strand):
@@ -516,7 +533,7 @@ __global__ void __launch_bounds__(FB_THREADS) st_stats_kernel(const FbArgs a)
                         s2 = flogsum(s2, jv, tbl);
                     }
                     if (s2 > log_p_j1) s2 = log_p_j1;
-                    const float p2 = __fsub_rn(expf(log_p_j1), expf(s2));
+                    const float p2 = __fsub_rn(nc_expf(log_p_j1), nc_expf(s2));
                     t_denom = log_p_j1;
                     t_stay = jj;
                     t_skip = logf(p2);

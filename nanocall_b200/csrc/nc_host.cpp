@@ -99,14 +99,18 @@ void nc_transition_lut(float p_stay, float p_skip, float* lut64)
 {
     float p_step = static_cast< float >(1.0 - p_stay - p_skip);
     float p_skip_1 = static_cast< float >(p_skip / (p_skip + 1.0));
+    // the double-valued terms do not depend on the mask: evaluate each pow once
+    double term[NC_KMER];
+    for (unsigned l = 2; l < NC_KMER; ++l) term[l] = std::pow(p_skip_1, l - 1) / (1u << (2 * l));
+    const double tail = (std::pow(p_skip_1, 5) / (1.0f - p_skip_1)) / NC_N_STATES;
     for (unsigned mask = 0; mask < 64; ++mask)
     {
         float p = 0;
         if (mask & 1u) p += p_stay;
         if (mask & 2u) p += p_step / 4;
         for (unsigned l = 2; l < NC_KMER; ++l)
-            if (mask & (1u << l)) p += std::pow(p_skip_1, l - 1) / (1u << (2 * l));
-        p += (std::pow(p_skip_1, 5) / (1.0f - p_skip_1)) / NC_N_STATES;
+            if (mask & (1u << l)) p += term[l];  // float += double: added in double, narrowed (as :139)
+        p += tail;
         lut64[mask] = std::log(p);
     }
 }

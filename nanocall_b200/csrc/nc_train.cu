@@ -53,6 +53,7 @@ int ensure_train_tables(nc_ctx* ctx)
         ctx->n_train_kmers = (unsigned)km.size();
     }
     NC_CUDA(ctx, cudaFuncSetAttribute(nc::fwbw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nc::fwbw_smem_bytes()));
+    NC_CUDA(ctx, cudaFuncSetAttribute(nc::pm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nc::pm_stats_smem_bytes()));
     NC_CUDA(ctx, cudaFuncSetAttribute(nc::st_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nc::st_stats_smem_bytes()));
     return NC_OK;
 }
@@ -243,7 +244,7 @@ int run_wave(nc_ctx* ctx, const Wave& w, const float* d_mean, const float* d_std
     NC_CUDA(ctx, cudaGetLastError());
     if (pm_stats)
     {
-        nc::pm_stats_kernel<<< dim3(tiles, ns), 512, 0, s >>>(a);
+        nc::pm_stats_kernel<<< dim3(tiles, ns), 512, nc::pm_stats_smem_bytes(), s >>>(a);
         NC_CUDA(ctx, cudaGetLastError());
     }
     if (st_stats && ng)
