@@ -1,0 +1,726 @@
+// See pipeline.hpp for the map onto the reference.  Every decision below (candidate lists, training
+// slices, EM stop rules, model selection, candidate ranking, FASTA naming) follows nanocall.cpp line
+// by line, but each "call Parameter_Trainer / Viterbi for this read" becomes "append a job to the batch".
+#include "pipeline.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <sstream>
+#include <stdexcept>
+
+namespace nchost {
+
+void log_line(int level, int threshold, const std::string& msg)
+{
+    if (level <= threshold) std::clog << msg << std::endl;
+}
+
+#define NLOG(lvl, expr)                                   \
+    do {                                                  \
+        if ((lvl) <= opt_.log_level) {                    \
+            std::ostringstream _o;                        \
+            _o << expr;                                   \
+            std::clog << _o.str() << std::endl;           \
+        }                                                 \
+    } while (0)
+
+static std::ostream& operator<<(std::ostream& os, const nc_pm_params& p)  // Pore_Model.hpp:66-71
+{
+    os << "[scale=" << p.scale << " shift=" << p.shift << " drift=" << p.drift
+       << " var=" << p.var << " scale_sd=" << p.scale_sd << " var_sd=" << p.var_sd << "]";
+    return os;
+}
+static std::ostream& operator<<(std::ostream& os, const nc_st_params& p)  // State_Transitions.hpp:39-44
+{
+    os << "[p_stay=" << p.p_stay << " p_skip=" << p.p_skip << "]";
+    return os;
+}
+
+static nc_pm_params default_pm()
+{
+    nc_pm_params p;
+    p.scale = 1.0f; p.shift = 0.0f; p.drift = 0.0f; p.var = 1.0f; p.scale_sd = 1.0f; p.var_sd = 1.0f;
+    return p;
+}
+
+Pipeline::Pipeline(const Options& o, int device) : opt_(o)
+{
+    if (opt_.train_drift < 0) opt_.train_drift = (opt_.pore == "r73") ? 1 : 0;  // nanocall.cpp:943-969
+    int rc = nc_ctx_create(device, 0, &ctx_);
+    if (rc != NC_OK) throw std::runtime_error(std::string("nc_ctx_create: ") + nc_last_error(nullptr));
+}
+
+Pipeline::~Pipeline() { nc_ctx_destroy(ctx_); }
+
+void Pipeline::check(int rc, const char* what) const
+{
+    if (rc != NC_OK) throw std::runtime_error(std::string(what) + ": " + nc_last_error(ctx_));
+}
+
+// ---------------------------------------------------------------- models (nanocall.cpp:97-178)
+static bool read_model_tsv(const std::string& path, std::vector< float >& table, std::string& err)
+{
+    // Pore_Model::operator>> (Pore_Model.hpp:251-287): "kmer level_mean level_stdv sd_mean sd_stdv", '#' and
+    // header lines skipped, rows sorted by k-mer
+    std::ifstream is(path);
+    if (!is) { err = "cannot open " + path; return false; }
+    table.assign(4 * NC_N_STATES, 0.f);
+    std::vector< bool > seen(NC_N_STATES, false);
+    std::string line;
+    unsigned n = 0;
+    while (std::getline(is, line))
+    {
+        std::istringstream iss(line);
+        std::string s;
+        iss >> s;
+        if (s.empty() || s[0] == '#') continue;
+        if (line.find("kmer") != std::string::npos) continue;
+        if (s.size() != NC_KMER) { err = "bad k-mer in " + path; return false; }
+        unsigned idx = 0;
+        for (char c : s)
+        {
+            int b = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+            if (b < 0) { err = "bad base in " + path; return false; }
+            idx = (idx << 2) | (unsigned)b;
+        }
+        float* row = table.data() + 4 * idx;
+        iss >> row[0] >> row[1] >> row[2] >> row[3];
+        if (!seen[idx]) { seen[idx] = true; ++n; }
+    }
+    if (n != NC_N_STATES) { err = "unexpected number of states in " + path; return false; }
+    return true;
+}
+
+void Pipeline::init_models()
+{
+    auto add = [&](const std::string& name, int strand, std::vector< float >&& table) {
+        Model m;
+        m.name = name;
+        m.strand = strand;
+        m.table = std::move(table);
+        check(nc_model_register(ctx_, m.table.data(), strand, &m.id), "nc_model_register");
+        check(nc_model_stats(ctx_, m.id, &m.mean, &m.stdv), "nc_model_stats");
+        NLOG(2, "loaded module [" << name << "] for strand [" << strand << "] statistics [mean=" << m.mean
+                                  << ", stdv=" << m.stdv << "]");
+        models_[name] = std::move(m);
+    };
+    if (!opt_.model_files.empty())
+    {
+        bool have[3] = { false, false, false };
+        for (const auto& s : opt_.model_files)
+        {
+            if (s.size() < 3 || (s[0] != '0' && s[0] != '1' && s[0] != '2') || s[1] != ':')
+                throw std::runtime_error("could not parse model name: \"" + s + "\"; format should be \"[0|1|2]:<file>\"");
+            int st = s[0] - '0';
+            have[st] = true;
+            std::vector< float > table;
+            std::string err;
+            if (!read_model_tsv(s.substr(2), table, err)) throw std::runtime_error(err);
+            add(s.substr(2), st, std::move(table));
+        }
+        if (!have[2] && (have[0] != have[1]))
+            throw std::runtime_error("models were specified only for one strand! give models for both strands, or for neither.");
+        return;
+    }
+    // builtin models: names filtered by "<pore>." prefix (nanocall.cpp:157-170)
+    std::string dir = opt_.data_dir;
+    std::ifstream names(dir + "/builtin_models.txt");
+    std::ifstream blob(dir + "/builtin_models.bin", std::ios::binary);
+    if (!names || !blob) throw std::runtime_error("builtin model data not found under " + dir);
+    std::string name;
+    int strand;
+    unsigned idx = 0;
+    while (names >> name >> strand)
+    {
+        std::vector< float > table(4 * NC_N_STATES);
+        blob.seekg((std::streamoff)idx * 4 * NC_N_STATES * sizeof(float));
+        blob.read(reinterpret_cast< char* >(table.data()), table.size() * sizeof(float));
+        if (!blob) throw std::runtime_error("builtin_models.bin is truncated");
+        ++idx;
+        if (name.compare(0, opt_.pore.size() + 1, opt_.pore + ".") != 0) continue;
+        add(name, strand, std::move(table));
+    }
+    if (models_.empty()) throw std::runtime_error("no builtin models found for pore [" + opt_.pore + "]");
+}
+
+// ---------------------------------------------------------------- initial scaling (Fast5_Summary.hpp:210-278)
+void Pipeline::init_read_params(Read& r) const
+{
+    r.pm_params_m.clear();
+    r.st_params_m.clear();
+    for (auto& k : r.preferred_model) k = Model_Key();
+    const nc_st_params dst = default_st();
+    r.scale_strands_together = opt_.double_strand_scaling
+        && r.events[0].size() >= opt_.min_ed_events && r.events[1].size() >= opt_.min_ed_events;
+    if (r.scale_strands_together)
+    {
+        float m0, s0, m1, s1;
+        nc_mean_stdv((uint32_t)r.events[0].size(), r.events[0].mean.data(), &m0, &s0);
+        nc_mean_stdv((uint32_t)r.events[1].size(), r.events[1].mean.data(), &m1, &s1);
+        for (const auto& p0 : models_)
+            if (p0.second.strand == 0 || p0.second.strand == 2)
+                for (const auto& p1 : models_)
+                    if (p1.second.strand == 1 || p1.second.strand == 2)
+                    {
+                        Model_Key key = { { p0.first, p1.first } };
+                        nc_pm_params pm = default_pm();
+                        pm.scale = (s0 / p0.second.stdv + s1 / p1.second.stdv) / 2;
+                        pm.shift = (m0 - pm.scale * p0.second.mean + m1 - pm.scale * p1.second.mean) / 2;
+                        r.pm_params_m[key] = pm;
+                        r.st_params_m[key] = { { dst, dst } };
+                    }
+    }
+    else
+    {
+        for (unsigned st = 0; st < 2; ++st)
+        {
+            if (r.events[st].size() < opt_.min_ed_events) continue;
+            float m, s;
+            nc_mean_stdv((uint32_t)r.events[st].size(), r.events[st].mean.data(), &m, &s);
+            for (const auto& p : models_)
+                if (p.second.strand == (int)st || p.second.strand == 2)
+                {
+                    Model_Key key;
+                    key[st] = p.first;
+                    nc_pm_params pm = default_pm();
+                    pm.scale = s / p.second.stdv;
+                    pm.shift = m - pm.scale * p.second.mean;
+                    r.pm_params_m[key] = pm;
+                    r.st_params_m[key] = { { dst, dst } };
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- training (nanocall.cpp:275-582)
+namespace {
+struct Candidate
+{
+    size_t read;
+    Model_Key key;
+    unsigned strand;           // 0/1 single-strand training, 2 = both strands scaled together
+    int model_id[2];
+    nc_pm_params crt_pm;
+    std::array< nc_st_params, 2 > crt_st;
+    float crt_fit;
+    unsigned round;
+    unsigned max_rounds;
+    bool active;
+    // packed training sequences of this candidate
+    std::vector< uint8_t > seq_strand;
+    std::vector< uint32_t > seq_len;
+    std::vector< float > mean, stdv, start;
+};
+} // namespace
+
+void Pipeline::train_reads(std::vector< Read* >& reads)
+{
+    std::vector< Candidate > cands;
+    for (size_t ri = 0; ri < reads.size(); ++ri)
+    {
+        Read& rd = *reads[ri];
+        // per-strand list of models to try (:300-323)
+        std::array< std::vector< std::string >, 2 > model_list;
+        for (unsigned st = 0; st < 2; ++st)
+        {
+            if (rd.events[st].size() < opt_.min_ed_events) continue;
+            if (!rd.preferred_model[st][st].empty()) model_list[st].push_back(rd.preferred_model[st][st]);
+            else
+                for (const auto& p : models_)
+                    if (p.second.strand == (int)st || p.second.strand == 2) model_list[st].push_back(p.first);
+        }
+        // two training sequences per strand: first and last n/2 events (:327-338)
+        auto add_seqs = [&](Candidate& c, unsigned st) {
+            const Strand_Events& ev = rd.events[st];
+            unsigned n = (unsigned)std::min< size_t >(opt_.scaling_num_events, ev.size());
+            unsigned h = n / 2;
+            size_t from[2] = { 0, ev.size() - h };
+            for (int part = 0; part < 2; ++part)
+            {
+                c.seq_strand.push_back((uint8_t)st);
+                c.seq_len.push_back(h);
+                c.mean.insert(c.mean.end(), ev.mean.begin() + from[part], ev.mean.begin() + from[part] + h);
+                c.stdv.insert(c.stdv.end(), ev.stdv.begin() + from[part], ev.stdv.begin() + from[part] + h);
+                c.start.insert(c.start.end(), ev.start.begin() + from[part], ev.start.begin() + from[part] + h);
+            }
+        };
+        auto make = [&](const Model_Key& key, unsigned strand) {
+            Candidate c;
+            c.read = ri;
+            c.key = key;
+            c.strand = strand;
+            c.crt_pm = rd.pm_params_m.at(key);
+            c.crt_st = rd.st_params_m.at(key);
+            c.crt_fit = -std::numeric_limits< float >::infinity();
+            c.round = 0;
+            c.active = true;
+            return c;
+        };
+        if (rd.scale_strands_together)
+        {
+            for (const auto& m0 : model_list[0])
+                for (const auto& m1 : model_list[1])
+                {
+                    Candidate c = make(Model_Key{ { m0, m1 } }, 2);
+                    c.model_id[0] = models_.at(m0).id;
+                    c.model_id[1] = models_.at(m1).id;
+                    c.max_rounds = 2u * opt_.scaling_max_rounds;  // :420
+                    add_seqs(c, 0);
+                    add_seqs(c, 1);
+                    cands.push_back(std::move(c));
+                }
+        }
+        else
+        {
+            for (unsigned st = 0; st < 2; ++st)
+            {
+                if (rd.events[st].size() < opt_.min_ed_events) continue;
+                for (const auto& m : model_list[st])
+                {
+                    Model_Key key;
+                    key[st] = m;
+                    Candidate c = make(key, st);
+                    c.model_id[0] = c.model_id[1] = models_.at(m).id;  // :491
+                    c.max_rounds = opt_.scaling_max_rounds;            // :536
+                    add_seqs(c, st);
+                    cands.push_back(std::move(c));
+                }
+            }
+        }
+    }
+    // drop candidates whose sequences are empty (n/2 == 0 cannot happen with min_ed_events >= 2, but be safe)
+    for (auto& c : cands)
+        for (auto l : c.seq_len)
+            if (l == 0) c.active = false;
+
+    nc_train_opts topts;
+    topts.train_scaling = opt_.train_scaling;
+    topts.train_transitions = opt_.train_transitions;
+    topts.train_drift = opt_.train_drift;
+
+    // ---- EM rounds: every active candidate advances by one train_one_round per batch call (:367-426, :483-542)
+    std::vector< size_t > act;
+    std::vector< uint32_t > seq_off;
+    std::vector< uint64_t > ev_off;
+    std::vector< uint8_t > strands;
+    std::vector< float > mean, stdv, start;
+    std::vector< nc_train_in > tin;
+    std::vector< nc_train_out > tout;
+    for (;;)
+    {
+        act.clear();
+        for (size_t k = 0; k < cands.size(); ++k)
+            if (cands[k].active) act.push_back(k);
+        if (act.empty()) break;
+        seq_off.assign(1, 0);
+        ev_off.assign(1, 0);
+        strands.clear(); mean.clear(); stdv.clear(); start.clear();
+        tin.resize(act.size());
+        tout.resize(act.size());
+        for (size_t a = 0; a < act.size(); ++a)
+        {
+            const Candidate& c = cands[act[a]];
+            for (size_t s = 0; s < c.seq_len.size(); ++s)
+            {
+                strands.push_back(c.seq_strand[s]);
+                ev_off.push_back(ev_off.back() + c.seq_len[s]);
+            }
+            seq_off.push_back(seq_off.back() + (uint32_t)c.seq_len.size());
+            mean.insert(mean.end(), c.mean.begin(), c.mean.end());
+            stdv.insert(stdv.end(), c.stdv.begin(), c.stdv.end());
+            start.insert(start.end(), c.start.begin(), c.start.end());
+            tin[a].model_id[0] = c.model_id[0];
+            tin[a].model_id[1] = c.model_id[1];
+            tin[a].pm = c.crt_pm;
+            tin[a].st[0] = c.crt_st[0];
+            tin[a].st[1] = c.crt_st[1];
+        }
+        check(nc_train_round_batch(ctx_, (uint32_t)act.size(), seq_off.data(), ev_off.data(), strands.data(),
+                                   mean.data(), stdv.data(), start.data(), tin.data(), &topts, tout.data()),
+              "nc_train_round_batch");
+        train_kernel_ms += nc_ctx_last_kernel_ms(ctx_);
+        ++train_rounds;
+        fwbw_events += ev_off.back();
+        for (size_t a = 0; a < act.size(); ++a)
+        {
+            Candidate& c = cands[act[a]];
+            const nc_pm_params old_pm = c.crt_pm;
+            const std::array< nc_st_params, 2 > old_st = c.crt_st;
+            const float old_fit = c.crt_fit;
+            c.crt_pm = tout[a].pm;
+            c.crt_st = { { tout[a].st[0], tout[a].st[1] } };
+            c.crt_fit = tout[a].fit;
+            const Read& rd = *reads[c.read];
+            NLOG(3, "scaling_round read [" << rd.read_id << "] strand [" << c.strand << "] model [" << c.key[0]
+                        << (c.strand == 2 ? "+" : "") << c.key[1] << "] old_pm_params [" << old_pm << "] old_fit ["
+                        << old_fit << "] crt_pm_params [" << c.crt_pm << "] crt_fit [" << c.crt_fit << "] round ["
+                        << c.round << "]");
+            if (tout[a].done) { c.active = false; continue; }  // singularity detected; stop
+            if (c.crt_fit < old_fit)
+            {
+                NLOG(2, "scaling_regression read [" << rd.read_id << "] strand [" << c.strand << "] model [" << c.key[0]
+                            << (c.strand == 2 ? "+" : "") << c.key[1] << "] old_params [" << old_pm << "] old_fit ["
+                            << old_fit << "] crt_pm_params [" << c.crt_pm << "] crt_fit [" << c.crt_fit
+                            << "] round [" << c.round << "]");
+                c.crt_pm = old_pm;
+                c.crt_st = old_st;
+                c.crt_fit = old_fit;
+                c.active = false;
+                continue;
+            }
+            ++c.round;
+            if (c.round >= c.max_rounds || (c.round > 1 && c.crt_fit < old_fit + opt_.scaling_min_progress)) c.active = false;
+        }
+    }
+    // ---- results back into the reads, model selection (:427-459, :543-570)
+    std::map< std::pair< size_t, unsigned >, std::vector< const Candidate* > > by_read;  // (read, strand tag) -> candidates in map order
+    for (auto& c : cands)
+    {
+        Read& rd = *reads[c.read];
+        rd.pm_params_m[c.key] = c.crt_pm;
+        rd.st_params_m[c.key] = c.crt_st;
+        if (c.strand == 2)
+            NLOG(2, "scaling_result read [" << rd.read_id << "] strand [2] model [" << c.key[0] << "+" << c.key[1]
+                        << "] pm_params [" << c.crt_pm << "] st_params [" << c.crt_st[0] << "," << c.crt_st[1]
+                        << "] fit [" << c.crt_fit << "] rounds [" << c.round << "]");
+        else
+            NLOG(2, "scaling_result read [" << rd.read_id << "] strand [" << c.strand << "] model [" << c.key[c.strand]
+                        << "] pm_params [" << c.crt_pm << "] st_params [" << c.crt_st[c.strand] << "] fit ["
+                        << c.crt_fit << "] rounds [" << c.round << "]");
+        by_read[std::make_pair(c.read, c.strand)].push_back(&c);
+    }
+    if (opt_.scaling_select_threshold < std::numeric_limits< float >::infinity())
+    {
+        for (auto& e : by_read)
+        {
+            // candidates were generated in the key order of the reference's std::map; alg::max_of keeps the first maximum
+            std::vector< const Candidate* > v = e.second;
+            std::sort(v.begin(), v.end(), [](const Candidate* a, const Candidate* b) { return a->key < b->key; });
+            const Candidate* best = v[0];
+            for (const Candidate* c : v)
+                if (best->crt_fit < c->crt_fit) best = c;
+            bool unique = true;
+            for (const Candidate* c : v)
+                if (c != best && !(c->crt_fit + opt_.scaling_select_threshold < best->crt_fit)) unique = false;
+            if (!unique) continue;
+            Read& rd = *reads[e.first.first];
+            if (e.first.second == 2)
+            {
+                rd.preferred_model[2] = best->key;
+                NLOG(2, "selected_model read [" << rd.read_id << "] strand [2] model [" << best->key[0] << "+" << best->key[1] << "]");
+            }
+            else
+            {
+                unsigned st = e.first.second;
+                rd.preferred_model[st][st] = best->key[st];
+                NLOG(2, "selected_model read [" << rd.read_id << "] strand [" << st << "] model [" << best->key[st] << "]");
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- basecalling (nanocall.cpp:593-869)
+namespace {
+struct VitJob
+{
+    size_t read;
+    unsigned strand;
+    Model_Key key;
+    size_t cand;  // candidate index within the read's list
+};
+} // namespace
+
+void Pipeline::basecall_reads(std::vector< Read* >& reads)
+{
+    const uint64_t max_events_per_call = 48ull << 20;
+    size_t r0 = 0;
+    while (r0 < reads.size())
+    {
+        std::vector< VitJob > jobs;
+        std::vector< uint64_t > off(1, 0);
+        std::vector< float > mean, stdv, start;
+        std::vector< int32_t > mid;
+        std::vector< nc_pm_params > pm;
+        std::vector< nc_st_params > st;
+        size_t r1 = r0;
+        while (r1 < reads.size() && (r1 == r0 || off.back() < max_events_per_call))
+        {
+            Read& rd = *reads[r1];
+            auto add_job = [&](unsigned s, const Model_Key& key, size_t cand) {
+                const Strand_Events& ev = rd.events[s];
+                const Model& m = models_.at(key[s]);
+                const nc_pm_params& p = rd.pm_params_m.at(key);
+                const nc_st_params& t = rd.st_params_m.at(key)[s];
+                NLOG(2, "basecalling read [" << rd.read_id << "] strand [" << s << "] model [" << key[s]
+                            << "] pm_params [" << p << "] st_params [" << t << "]");
+                // means_apart check (:633-683): mean of the scaled model's level means vs mean of the events
+                {
+                    std::vector< float > lv(NC_N_STATES);
+                    for (unsigned j = 0; j < NC_N_STATES; ++j) lv[j] = m.table[4 * j] * p.scale + p.shift;
+                    float mm, ms, em, es;
+                    nc_mean_stdv(NC_N_STATES, lv.data(), &mm, &ms);
+                    nc_mean_stdv((uint32_t)ev.size(), ev.mean.data(), &em, &es);
+                    if (std::abs(em - mm) > 5.0)
+                        NLOG(1, "means_apart read [" << rd.read_id << "] strand [" << s << "] model [" << key[s]
+                                    << "] parameters [" << p << "] model_mean=[" << mm << "] events_mean=[" << em << "]");
+                }
+                jobs.push_back(VitJob{ r1, s, key, cand });
+                mean.insert(mean.end(), ev.mean.begin(), ev.mean.end());
+                stdv.insert(stdv.end(), ev.stdv.begin(), ev.stdv.end());
+                start.insert(start.end(), ev.start.begin(), ev.start.end());
+                off.push_back(off.back() + ev.size());
+                mid.push_back(m.id);
+                pm.push_back(p);
+                st.push_back(t);
+            };
+            if (rd.scale_strands_together)
+            {
+                std::vector< Model_Key > sub;  // :697-709
+                if (!rd.preferred_model[2][0].empty()) sub.push_back(rd.preferred_model[2]);
+                else
+                    for (const auto& p : rd.pm_params_m)
+                        if (!p.first[0].empty() && !p.first[1].empty()) sub.push_back(p.first);
+                for (size_t c = 0; c < sub.size(); ++c)
+                    for (unsigned s = 0; s < 2; ++s) add_job(s, sub[c], c);
+            }
+            else
+            {
+                for (unsigned s = 0; s < 2; ++s)
+                {
+                    if (rd.events[s].size() < opt_.min_ed_events) continue;
+                    std::vector< Model_Key > sub;  // :791-806
+                    if (!rd.preferred_model[s][s].empty()) sub.push_back(rd.preferred_model[s]);
+                    else
+                        for (const auto& p : rd.pm_params_m)
+                            if (!p.first[s].empty() && p.first[1 - s].empty()) sub.push_back(p.first);
+                    for (size_t c = 0; c < sub.size(); ++c) add_job(s, sub[c], c);
+                }
+            }
+            ++r1;
+        }
+        const uint32_t nj = (uint32_t)jobs.size();
+        std::vector< float > path(nj);
+        std::vector< uint16_t > states(off.back());
+        std::vector< uint8_t > moves(off.back());
+        if (nj)
+        {
+            check(nc_viterbi_packed(ctx_, nj, off.data(), mean.data(), stdv.data(), start.data(), nullptr, mid.data(),
+                                    pm.data(), st.data(), NC_MEM_HOST, path.data(), states.data(), moves.data()),
+                  "nc_viterbi_packed");
+            viterbi_kernel_ms += nc_ctx_last_kernel_ms(ctx_);
+            viterbi_events += off.back();
+        }
+        // ---- rank candidates per read (:711-750, :808-836)
+        auto seq_of = [&](size_t j) {
+            uint32_t n = (uint32_t)(off[j + 1] - off[j]);
+            uint32_t need = nc_base_seq(n, states.data() + off[j], moves.data() + off[j], nullptr, 0);
+            std::string s(need, 'N');
+            nc_base_seq(n, states.data() + off[j], moves.data() + off[j], &s[0], need);
+            return s;
+        };
+        size_t j = 0;
+        while (j < jobs.size())
+        {
+            Read& rd = *reads[jobs[j].read];
+            size_t je = j;
+            while (je < jobs.size() && jobs[je].read == jobs[j].read) ++je;
+            if (rd.scale_strands_together)
+            {
+                // jobs come in (strand 0, strand 1) pairs per candidate; best = last of a stable ascending sort by the sum
+                size_t best = j;
+                float best_sum = path[j] + path[j + 1];
+                for (size_t q = j + 2; q < je; q += 2)
+                {
+                    float s = path[q] + path[q + 1];
+                    if (!(s < best_sum)) { best = q; best_sum = s; }
+                }
+                const Model_Key key = jobs[best].key;
+                const nc_pm_params best_pm = rd.pm_params_m.at(key);
+                const std::array< nc_st_params, 2 > best_st = rd.st_params_m.at(key);
+                for (unsigned s = 0; s < 2; ++s)
+                {
+                    NLOG(2, "best_model read [" << rd.read_id << "] strand [" << s << "] model [" << key[s] << "] pm_params ["
+                                << best_pm << "] st_params [" << best_st[s] << "] log_path_prob [" << path[best + s] << "]");
+                    rd.preferred_model[s][s] = key[s];
+                    rd.pm_params_m[rd.preferred_model[s]] = best_pm;
+                    rd.st_params_m[rd.preferred_model[s]][s] = best_st[s];
+                    rd.base_seq[s] = seq_of(best + s);
+                    rd.log_path_prob[s] = path[best + s];
+                    rd.called[s] = true;
+                }
+            }
+            else
+            {
+                for (unsigned s = 0; s < 2; ++s)
+                {
+                    size_t best = SIZE_MAX;
+                    for (size_t q = j; q < je; ++q)
+                        if (jobs[q].strand == s && (best == SIZE_MAX || !(path[q] < path[best]))) best = q;
+                    if (best == SIZE_MAX) continue;
+                    const Model_Key key = jobs[best].key;
+                    NLOG(2, "best_model read [" << rd.read_id << "] strand [" << s << "] model [" << key[s] << "] pm_params ["
+                                << rd.pm_params_m.at(key) << "] st_params [" << rd.st_params_m.at(key)[s]
+                                << "] log_path_prob [" << path[best] << "]");
+                    rd.preferred_model[s][s] = key[s];
+                    rd.base_seq[s] = seq_of(best);
+                    rd.log_path_prob[s] = path[best];
+                    rd.called[s] = true;
+                }
+            }
+            j = je;
+        }
+        r0 = r1;
+    }
+}
+
+void Pipeline::write_fasta(std::ostream& os, const std::string& name, const std::string& seq, unsigned width)
+{
+    os << ">" << name << "\n";  // nanocall.cpp:584-591
+    for (size_t pos = 0; pos < seq.size(); pos += width) os << seq.substr(pos, width) << "\n";
+}
+
+void Pipeline::write_output(std::ostream& os, const Read& r) const
+{
+    for (unsigned st = 0; st < 2; ++st)
+    {
+        if (!r.called[st]) continue;
+        std::ostringstream name;
+        name << r.read_id << ":" << r.base_file_name << ":" << st;  // :764-769
+        write_fasta(os, name.str(), r.base_seq[st], opt_.fasta_line_width);
+    }
+}
+
+void Pipeline::write_stats_header(std::ostream& os)
+{
+    // Fast5_Summary::write_tsv_header (Fast5_Summary.hpp:460-476)
+    os << "file_name\tread_name\tnum_ed_events\tabasic_level\ttemplate_start_idx\ttemplate_end_idx"
+       << "\tcomplement_start_idx\tcomplement_end_idx";
+    for (unsigned st = 0; st < 2; ++st)
+        os << "\tn" << st << "_model_name\tn" << st << "_scale\tn" << st << "_shift\tn" << st << "_drift\tn" << st
+           << "_var\tn" << st << "_scale_sd\tn" << st << "_var_sd\tn" << st << "_p_stay\tn" << st << "_p_skip";
+    os << "\n";
+}
+
+void Pipeline::write_stats(std::ostream& os, const Read& r) const
+{
+    // Fast5_Summary::write_tsv (:478-502).  Event tables carry no raw-event indices: the strand bounds are the
+    // offsets of the two strands in the concatenated table, abasic_level is 0.
+    const size_t n0 = r.events[0].size(), n1 = r.events[1].size();
+    os << r.base_file_name << '\t' << r.read_id << '\t' << (n0 + n1) << '\t' << 0 << '\t' << 0 << '\t' << n0 << '\t' << n0
+       << '\t' << (n0 + n1);
+    auto pm_tsv = [&](const nc_pm_params& p) {
+        os << std::fixed << std::setprecision(5) << p.scale << '\t' << p.shift << '\t' << p.drift << '\t' << p.var << '\t'
+           << p.scale_sd << '\t' << p.var_sd;
+    };
+    auto st_tsv = [&](const nc_st_params& p) { os << std::fixed << std::setprecision(5) << p.p_stay << '\t' << p.p_skip; };
+    for (unsigned st = 0; st < 2; ++st)
+    {
+        os << '\t';
+        if (!r.preferred_model[st][st].empty() && r.pm_params_m.count(r.preferred_model[st]))
+        {
+            os << r.preferred_model[st][st] << '\t';
+            pm_tsv(r.pm_params_m.at(r.preferred_model[st]));
+            os << '\t';
+            st_tsv(r.st_params_m.at(r.preferred_model[st])[st]);
+        }
+        else
+        {
+            os << ".\t";
+            pm_tsv(default_pm());
+            os << '\t';
+            st_tsv(default_st());
+        }
+    }
+    os << "\n";
+    os.unsetf(std::ios_base::floatfield);
+}
+
+// ---------------------------------------------------------------- event tables
+bool load_events_tsv(const std::string& path, Read& r, std::string& err)
+{
+    // "#read_id <id>" header (optional), then rows "strand mean stdv start length"; the last four columns are what
+    // Event::operator>> reads (Event.hpp:59-68).  start is in seconds from the strand start the reference would use
+    // (Fast5_Summary.hpp:359).
+    std::ifstream is(path);
+    if (!is) { err = "cannot open " + path; return false; }
+    auto pos = path.find_last_of('/');
+    r.base_file_name = pos != std::string::npos ? path.substr(pos + 1) : path;
+    for (const char* ext : { ".events.tsv", ".tsv", ".txt" })
+    {
+        std::string e(ext);
+        if (r.base_file_name.size() > e.size() && r.base_file_name.compare(r.base_file_name.size() - e.size(), e.size(), e) == 0)
+        {
+            r.base_file_name.resize(r.base_file_name.size() - e.size());
+            break;
+        }
+    }
+    r.read_id = r.base_file_name;
+    std::string line;
+    while (std::getline(is, line))
+    {
+        if (line.empty()) continue;
+        if (line[0] == '#')
+        {
+            std::istringstream iss(line.substr(1));
+            std::string k, v;
+            iss >> k >> v;
+            if (k == "read_id" && !v.empty()) r.read_id = v;
+            continue;
+        }
+        std::istringstream iss(line);
+        unsigned st;
+        float mean, stdv, start, length;
+        if (!(iss >> st >> mean >> stdv >> start >> length) || st > 1) { err = "bad event row in " + path + ": " + line; return false; }
+        Strand_Events& ev = r.events[st];
+        ev.mean.push_back(mean); ev.stdv.push_back(stdv); ev.start.push_back(start); ev.length.push_back(length);
+    }
+    return true;
+}
+
+bool load_events_ncev(const std::string& path, std::vector< Read >& reads, std::string& err)
+{
+    // binary container: "NCEV0001", u32 n_reads, then per read: u32 id_len, id, u32 n0, u32 n1,
+    // and for each strand mean[n] stdv[n] start[n] length[n] as float32
+    std::ifstream is(path, std::ios::binary);
+    if (!is) { err = "cannot open " + path; return false; }
+    char magic[8];
+    uint32_t n_reads = 0;
+    is.read(magic, 8);
+    is.read(reinterpret_cast< char* >(&n_reads), 4);
+    if (!is || std::memcmp(magic, "NCEV0001", 8) != 0) { err = path + " is not an NCEV0001 file"; return false; }
+    auto pos = path.find_last_of('/');
+    std::string base = pos != std::string::npos ? path.substr(pos + 1) : path;
+    if (base.size() > 5 && base.compare(base.size() - 5, 5, ".ncev") == 0) base.resize(base.size() - 5);
+    for (uint32_t k = 0; k < n_reads; ++k)
+    {
+        Read r;
+        uint32_t id_len = 0, n[2] = { 0, 0 };
+        is.read(reinterpret_cast< char* >(&id_len), 4);
+        if (!is || id_len > 4096) { err = "corrupt read header in " + path; return false; }
+        r.read_id.resize(id_len);
+        is.read(&r.read_id[0], id_len);
+        is.read(reinterpret_cast< char* >(n), 8);
+        r.base_file_name = base;
+        for (int st = 0; st < 2; ++st)
+        {
+            Strand_Events& ev = r.events[st];
+            for (std::vector< float >* v : { &ev.mean, &ev.stdv, &ev.start, &ev.length })
+            {
+                v->resize(n[st]);
+                is.read(reinterpret_cast< char* >(v->data()), (std::streamsize)n[st] * sizeof(float));
+            }
+        }
+        if (!is) { err = "truncated " + path; return false; }
+        reads.push_back(std::move(r));
+    }
+    return true;
+}
+
+} // namespace nchost

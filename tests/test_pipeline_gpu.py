@@ -1,0 +1,133 @@
+"""Full pipeline (configs 3 and 4 of BASELINE.json in miniature): the nanocall-b200 CLI -- training rounds,
+model selection, Viterbi with the trained parameters, FASTA -- against the reference's driver logic restated
+over the oracle (tests/oracle_pipeline.py).  Basecalls must be identical, trained scaling parameters within 1e-4
+relative (north_star), fits within 1e-5 relative."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_pipeline as OP
+from nanocall_b200 import evio, synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "nanocall_b200", "bin", "nanocall-b200")
+R73 = ["r73.t.006.ont.model", "r73.c.p1.006.ont.model", "r73.c.p2.006.ont.model"]
+
+
+def _make_reads(models, seed, n_reads, nt=600, nc=500, comp="r73.c.p1.006.ont.model"):
+    rng = np.random.default_rng(seed)
+    reads = []
+    for k in range(n_reads):
+        pm = tuple(synth.random_params(rng, 1)[0])
+        t = synth.make_read(rng, models[R73[0]]["table"], nt + 17 * k, pm)
+        c = synth.make_read(rng, models[comp if k % 2 == 0 else R73[2]]["table"], nc + 11 * k, pm)
+        # complement starts where the template ended (start is relative to the template start when scaled together)
+        c["start"] = (c["start"] + t["start"][-1] + np.float32(0.5)).astype(np.float32)
+        reads.append((f"read{k}", [t, c]))
+    return reads
+
+
+def _run_cli(tmp_path, reads, extra):
+    path = os.path.join(tmp_path, "batch.ncev")
+    evio.write_ncev(path, reads)
+    out = os.path.join(tmp_path, "out.fa")
+    stats = os.path.join(tmp_path, "stats.tsv")
+    cmd = [CLI, "--pore", "r73", "-o", out, "--stats", stats, "--log", "info"] + extra + [path]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    fa, name = {}, None
+    for line in open(out):
+        line = line.strip()
+        if line.startswith(">"):
+            name = line[1:]
+            fa[name] = ""
+        else:
+            assert len(line) <= 80
+            fa[name] += line
+    return fa, p.stderr, open(stats).read()
+
+
+def _parse_scaling(stderr):
+    res = {}
+    pat = re.compile(r"scaling_result read \[(\S+)\] strand \[(\d)\] model \[(\S+)\] pm_params \[\[scale=(\S+) shift=(\S+) "
+                     r"drift=(\S+) var=(\S+) scale_sd=(\S+) var_sd=(\S+)\]\] st_params \[(.*)\] fit \[(\S+)\] rounds \[(\d+)\]")
+    for m in pat.finditer(stderr):
+        res[(m.group(1), int(m.group(2)), m.group(3))] = dict(
+            pm=np.array([float(m.group(i)) for i in range(4, 10)]), fit=float(m.group(11)), rounds=int(m.group(12)))
+    return res
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-2))
+
+
+def test_double_strand_pipeline(tmp_path, port, models):
+    mdl = {n: models[n] for n in R73}
+    reads = _make_reads(models, 3, 3)
+    extra = ["--scaling-num-events", "60", "--scaling-max-rounds", "3"]
+    fa, stderr, stats = _run_cli(str(tmp_path), reads, extra)
+    sc = _parse_scaling(stderr)
+    opts = OP.Opts()
+    opts.scaling_num_events, opts.scaling_max_rounds = 60, 3
+    for rid, ev in reads:
+        exp = OP.run_read(port, mdl, ev, opts)
+        assert exp["together"]
+        for key, pm in exp["pm_params"].items():
+            got = sc[(rid, 2, key[0] + "+" + key[1])]
+            assert got["rounds"] == exp["rounds"][key], (rid, key)
+            assert abs(got["fit"] - float(exp["fits"][key])) <= 1e-5 * abs(float(exp["fits"][key])) + 1e-3
+            # the log prints 6 significant digits; 1e-4 relative is north_star's bound
+            assert _rel(got["pm"], pm) < 1e-4 + 2e-6, (rid, key, got["pm"], pm)
+        for st in range(2):
+            name = f"{rid}:batch:{st}"
+            assert fa[name] == exp["calls"][st]["bases"], (rid, st)
+        sel = exp["preferred"][2]
+        assert (f"selected_model read [{rid}] strand [2]" in stderr) == (sel is not None)
+        if sel is not None:
+            assert f"selected_model read [{rid}] strand [2] model [{sel[0]}+{sel[1]}]" in stderr
+    assert stats.count("\n") == 1 + len(reads)
+
+
+def test_single_strand_and_no_train(tmp_path, port, models):
+    mdl = {n: models[n] for n in R73}
+    reads = _make_reads(models, 5, 2, nt=400, nc=300)
+    reads.append(("template_only", [reads[0][1][0], None]))
+    extra = ["--single-strand-scaling", "--scaling-num-events", "50", "--scaling-max-rounds", "2"]
+    fa, stderr, _ = _run_cli(str(tmp_path), reads, extra)
+    opts = OP.Opts()
+    opts.scaling_num_events, opts.scaling_max_rounds, opts.double_strand_scaling = 50, 2, False
+    for rid, ev in reads:
+        exp = OP.run_read(port, mdl, ev, opts)
+        assert not exp["together"]
+        for st, call in exp["calls"].items():
+            assert fa[f"{rid}:batch:{st}"] == call["bases"], (rid, st)
+        assert (f"{rid}:batch:1" in fa) == (1 in exp["calls"])
+    # --no-train: initial scaling only, every applicable model scored by Viterbi, best path probability wins
+    fa2, stderr2, _ = _run_cli(str(tmp_path), reads[:2], ["--no-train"])
+    for rid, ev in reads[:2]:
+        exp = OP.run_read(port, mdl, ev, OP.Opts(), train=False)
+        for st, call in exp["calls"].items():
+            assert fa2[f"{rid}:batch:{st}"] == call["bases"], (rid, st)
+            assert f"best_model read [{rid}] strand [{st}] model [{call['model']}]" in stderr2
+
+
+def test_events_tsv_input(tmp_path, port, models):
+    mdl = {n: models[n] for n in R73}
+    rd = _make_reads(models, 9, 1, nt=300, nc=250)[0]
+    path = os.path.join(str(tmp_path), "one.events.tsv")
+    evio.write_events_tsv(path, "tsvread", rd[1])
+    out = os.path.join(str(tmp_path), "o.fa")
+    p = subprocess.run([CLI, "--pore", "r73", "--no-train", "-o", out, "--log", "warning", str(tmp_path)],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    exp = OP.run_read(port, mdl, rd[1], OP.Opts(), train=False)
+    text = open(out).read().split("\n")
+    assert text[0] == ">tsvread:one:0"
+    seqs = "".join(text).split(">")
+    assert seqs[1].replace("tsvread:one:0", "") == exp["calls"][0]["bases"]
