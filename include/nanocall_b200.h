@@ -75,8 +75,8 @@ typedef struct { float p_stay, p_skip; } nc_st_params;
  *
  * Packed form.  Job k owns events [ev_off[k], ev_off[k+1]) of the concatenated event arrays:
  *   mean, stdv, start : Event::mean / stdv / start (Event.hpp:20-23; start in seconds from strand start)
- *   log_stdv          : Event::log_stdv = logf(stdv) after the stdv==0 -> 0.01 fix (Event.hpp:39-43);
- *                       may be NULL when mem == NC_MEM_HOST (computed on the host with libm then)
+ *   log_stdv          : Event::log_stdv = logf(stdv) after the stdv==0 -> 0.01 fix (Event.hpp:39-43); may be NULL,
+ *                       the kernels then derive it on the device with a bit-compatible port of glibc's logf
  * ev_off, model_id, pm, st and path_logprob are always host arrays; the event arrays and
  * states/moves live where `mem` says.
  * Outputs: path_logprob[k] = Viterbi::path_probability(); states[i] = Event::model_state_idx;

@@ -149,8 +149,6 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     if (n_jobs == 0) return NC_OK;
     if (!ev_off || !mean || !stdv || !start || !model_id || !pm || !st || !path_logprob)
         NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_packed: NULL argument");
-    if (mem == NC_MEM_DEVICE && !log_stdv)
-        NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_packed: log_stdv is required for device-resident events");
     if (moves && !states && mem == NC_MEM_DEVICE)
         NC_FAIL(ctx, NC_ERR_ARG, "nc_viterbi_packed: moves need states for device-resident outputs");
     if (ctx->models.empty()) NC_FAIL(ctx, NC_ERR_STATE, "nc_viterbi_packed: no model registered");
@@ -220,29 +218,22 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     a.log_2pi = (float)std::log(2.0 * M_PI);
     a.log_n_states = std::log((float)NC_N_STATES);
 
-    std::vector< float > lstd_host;
     const uint64_t base = ev_off[0];
     if (mem == NC_MEM_HOST)
     {
-        const float* lsp = log_stdv ? log_stdv + base : nullptr;
-        if (!lsp)
-        {
-            lstd_host.resize(total);
-            nc::host_event_logs(total, stdv + base, lstd_host.data(), ctx->host_threads);
-            lsp = lstd_host.data();
-        }
+        const float* lsp = log_stdv ? log_stdv + base : nullptr;  // NULL: the kernel derives it (nc_logf)
         if ((rc = dev_reserve(ctx, ctx->mean, total * sizeof(float))) != NC_OK) return rc;
         if ((rc = dev_reserve(ctx, ctx->stdv, total * sizeof(float))) != NC_OK) return rc;
         if ((rc = dev_reserve(ctx, ctx->start, total * sizeof(float))) != NC_OK) return rc;
-        if ((rc = dev_reserve(ctx, ctx->lstd, total * sizeof(float))) != NC_OK) return rc;
+        if (lsp && (rc = dev_reserve(ctx, ctx->lstd, total * sizeof(float))) != NC_OK) return rc;
         NC_CUDA(ctx, cudaMemcpyAsync(ctx->mean.p, mean + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
         NC_CUDA(ctx, cudaMemcpyAsync(ctx->stdv.p, stdv + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
         NC_CUDA(ctx, cudaMemcpyAsync(ctx->start.p, start + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
-        NC_CUDA(ctx, cudaMemcpyAsync(ctx->lstd.p, lsp, total * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (lsp) NC_CUDA(ctx, cudaMemcpyAsync(ctx->lstd.p, lsp, total * sizeof(float), cudaMemcpyHostToDevice, s));
         a.mean = (const float*)ctx->mean.p;
         a.stdv = (const float*)ctx->stdv.p;
         a.start = (const float*)ctx->start.p;
-        a.log_stdv = (const float*)ctx->lstd.p;
+        a.log_stdv = lsp ? (const float*)ctx->lstd.p : nullptr;
         a.states = nullptr;
         a.moves = nullptr;
         if (states || moves)
@@ -261,7 +252,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         a.mean = mean + base;
         a.stdv = stdv + base;
         a.start = start + base;
-        a.log_stdv = log_stdv + base;
+        a.log_stdv = log_stdv ? log_stdv + base : nullptr;
         a.states = states ? states + base : nullptr;
         a.moves = moves ? moves + base : nullptr;
     }

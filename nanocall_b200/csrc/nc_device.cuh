@@ -158,6 +158,82 @@ __device__ __forceinline__ float nc_expf(float x)
     return (float)y;
 }
 
+
+// logf with the bits of glibc 2.39's logf (sysdeps/ieee754/flt-32/e_logf.c): 16-entry {1/c, log c} table, cubic in
+// double.  The 36 doubles are glibc's __logf_data (16 x {invc, logc}, ln2, poly[3]) dumped from libm-2.39.a
+// (tools/logf_data.inc); the C twin tools/check_logf.c agrees with libm's logf on 35e6 sampled floats.  Used for
+// Event::log_stdv (Event.hpp:43) when the caller does not supply it and for Parameter_Trainer.hpp:512.
+__device__ const unsigned long long nc_logf_data[36] = {
+0x3ff661ec79f8f3beULL,
+0xbfd57bf7808caadeULL,
+0x3ff571ed4aaf883dULL,
+0xbfd2bef0a7c06ddbULL,
+0x3ff49539f0f010b0ULL,
+0xbfd01eae7f513a67ULL,
+0x3ff3c995b0b80385ULL,
+0xbfcb31d8a68224e9ULL,
+0x3ff30d190c8864a5ULL,
+0xbfc6574f0ac07758ULL,
+0x3ff25e227b0b8ea0ULL,
+0xbfc1aa2bc79c8100ULL,
+0x3ff1bb4a4a1a343fULL,
+0xbfba4e76ce8c0e5eULL,
+0x3ff12358f08ae5baULL,
+0xbfb1973c5a611cccULL,
+0x3ff0953f419900a7ULL,
+0xbfa252f438e10c1eULL,
+0x3ff0000000000000ULL,
+0x0000000000000000ULL,
+0x3fee608cfd9a47acULL,
+0x3faaa5aa5df25984ULL,
+0x3feca4b31f026aa0ULL,
+0x3fbc5e53aa362eb4ULL,
+0x3feb2036576afce6ULL,
+0x3fc526e57720db08ULL,
+0x3fe9c2d163a1aa2dULL,
+0x3fcbc2860d224770ULL,
+0x3fe886e6037841edULL,
+0x3fd1058bc8a07ee1ULL,
+0x3fe767dcf5534862ULL,
+0x3fd4043057b6ee09ULL,
+0x3fe62e42fefa39efULL,
+0xbfd00ea348b88334ULL,
+0x3fd5575b0be00b6aULL,
+0xbfdffffef20a4123ULL
+};
+
+__device__ __forceinline__ float nc_logf(float x)
+{
+    unsigned ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u)
+    {
+        if (ix * 2u == 0u) return NC_NEG_INF;                       // log(+-0) = -inf
+        if (ix == 0x7f800000u) return x;                            // log(inf) = inf
+        if ((ix & 0x80000000u) || ix * 2u >= 0xff000000u) return __int_as_float(0x7fc00000);  // x < 0 or NaN
+        ix = __float_as_uint(__fmul_rn(x, 0x1p23f));                // subnormal: normalise
+        ix -= 23u << 23;
+    }
+    const unsigned tmp = ix - 0x3f330000u;
+    const int i = (tmp >> 19) & 15;
+    const int k = (int)tmp >> 23;
+    const unsigned iz = ix - (tmp & 0xff800000u);
+    const double invc = __longlong_as_double((long long)__ldg(nc_logf_data + 2 * i));
+    const double logc = __longlong_as_double((long long)__ldg(nc_logf_data + 2 * i + 1));
+    const double ln2 = __longlong_as_double((long long)__ldg(nc_logf_data + 32));
+    const double a0 = __longlong_as_double((long long)__ldg(nc_logf_data + 33));
+    const double a1 = __longlong_as_double((long long)__ldg(nc_logf_data + 34));
+    const double a2 = __longlong_as_double((long long)__ldg(nc_logf_data + 35));
+    const double z = (double)__uint_as_float(iz);
+    const double r = __dsub_rn(__dmul_rn(z, invc), 1.0);
+    const double y0 = __dadd_rn(logc, __dmul_rn((double)k, ln2));
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(a1, r), a2);
+    y = __dadd_rn(__dmul_rn(a0, r2), y);
+    y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+    return (float)y;
+}
+
 // Backpointer byte -> predecessor state.  0..15: two-step predecessor (bb<<8)|(j>>4);
 // 16..19: one-step predecessor (b<<10)|(j>>2); 20: j itself.
 __device__ __forceinline__ unsigned bp_decode(unsigned code, unsigned j)

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(FB_THREADS) emission_kernel(const FbArgs a)
             const float stdv = __ldg(a.stdv + e);
             const float y = (stdv == 0.0f) ? 0.01f : stdv;                                  // Event.hpp:39-42
             const float x = __fsub_rn(__ldg(a.mean + e), __fmul_rn(J.drift, __ldg(a.start + e)));  // Event.hpp:81
-            const float ly3 = __fmul_rn(3.0f, __ldg(a.log_stdv + e));
+            const float ly3 = __fmul_rn(3.0f, a.log_stdv ? __ldg(a.log_stdv + e) : nc_logf(y));
             const float ry = __frcp_rn(y);
             float4 o;
             o.x = emission(P[0], x, y, ly3, ry, a.log_2pi);
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(FB_THREADS) st_stats_kernel(const FbArgs a)
                     const float p2 = __fsub_rn(nc_expf(log_p_j1), nc_expf(s2));
                     t_denom = log_p_j1;
                     t_stay = jj;
-                    t_skip = logf(p2);
+                    t_skip = nc_logf(p2);
                 }
                 term[0][t] = t_denom;
                 term[1][t] = t_stay;

@@ -276,18 +276,14 @@ int upload_events(nc_ctx* ctx, size_t total, const float* mean, const float* std
                   std::vector< float >& y_fixed)
 {
     int rc;
-    std::vector< float > lstd(total);
-    nc::host_event_logs(total, stdv, lstd.data(), ctx->host_threads);
     y_fixed.resize(total);
     for (size_t i = 0; i < total; ++i) y_fixed[i] = (stdv[i] == 0.0f) ? 0.01f : stdv[i];
     if ((rc = dev_reserve(ctx, ctx->fb_mean, total * sizeof(float))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->fb_stdv, total * sizeof(float))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->fb_start, total * sizeof(float))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->fb_lstd, total * sizeof(float))) != NC_OK) return rc;
     NC_CUDA(ctx, cudaMemcpy(ctx->fb_mean.p, mean, total * sizeof(float), cudaMemcpyHostToDevice));
     NC_CUDA(ctx, cudaMemcpy(ctx->fb_stdv.p, stdv, total * sizeof(float), cudaMemcpyHostToDevice));
     NC_CUDA(ctx, cudaMemcpy(ctx->fb_start.p, start, total * sizeof(float), cudaMemcpyHostToDevice));
-    NC_CUDA(ctx, cudaMemcpy(ctx->fb_lstd.p, lstd.data(), total * sizeof(float), cudaMemcpyHostToDevice));
     return NC_OK;
 }
 
@@ -318,7 +314,7 @@ int nc_fwbw(nc_ctx* ctx, int32_t model_id, const nc_pm_params* pm, const nc_st_p
     w.max_len = n_events;
     std::vector< float > lz, pmr, sta;
     if ((rc = run_wave(ctx, w, (const float*)ctx->fb_mean.p, (const float*)ctx->fb_stdv.p, (const float*)ctx->fb_start.p,
-                       (const float*)ctx->fb_lstd.p, false, false, lz, pmr, sta)) != NC_OK)
+                       nullptr, false, false, lz, pmr, sta)) != NC_OK)
         return rc;
     const size_t cells = (size_t)n_events * NC_N_STATES;
     const float* sc = (const float*)ctx->fb_scratch.p;
@@ -403,7 +399,7 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
             ++g1;
         }
         if ((rc = run_wave(ctx, w, (const float*)ctx->fb_mean.p, (const float*)ctx->fb_stdv.p, (const float*)ctx->fb_start.p,
-                           (const float*)ctx->fb_lstd.p, opts->train_scaling != 0, opts->train_transitions != 0,
+                           nullptr, opts->train_scaling != 0, opts->train_transitions != 0,
                            lz, pm_rows, st_acc)) != NC_OK)
             return rc;
         // ---- finish every group of the wave on the host (train_one_round, :541-579)

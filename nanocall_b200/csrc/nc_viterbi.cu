@@ -61,7 +61,7 @@ __device__ __forceinline__ EvRegs ev_load(const VitArgs& a, unsigned long long o
         r.mean = __ldg(a.mean + off + i);
         r.stdv = __ldg(a.stdv + off + i);
         r.start = __ldg(a.start + off + i);
-        r.lstd = __ldg(a.log_stdv + off + i);
+        r.lstd = a.log_stdv ? __ldg(a.log_stdv + off + i) : nc_logf(r.stdv == 0.0f ? 0.01f : r.stdv);
     }
     else { r.mean = 0.f; r.stdv = 1.f; r.start = 0.f; r.lstd = 0.f; }
     return r;

@@ -11,7 +11,7 @@ from nanocall_b200 import synth
 pytestmark = pytest.mark.gpu
 
 T, C1, C2 = "r73.t.006.ont.model", "r73.c.p1.006.ont.model", "r73.c.p2.006.ont.model"
-RTOL = 1e-5
+RTOL = 2e-7  # a couple of float ulps: the round is reproduced essentially bit for bit
 
 
 def _close(a, b, rtol=RTOL):
