@@ -176,6 +176,7 @@ def main():
     import torch
     import torch.distributed as dist
     from nanocall_b200 import api, synth, models
+    from nanocall_b200 import dist as ncd
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: nanocall_b200 has no CPU path")
@@ -258,12 +259,10 @@ def main():
             raise SystemExit("e2e and device-resident paths disagree")
         e2e = (e2e_s, total * 16 + n * (288 + 4), total * 3 + n * 4)
 
-    if world > 1:
-        tt = torch.tensor([ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt[0])
-        if e2e:
-            e2e = (float(tt[1]),) + e2e[1:]
+    # whole-job numbers: every rank decoded `total` events; the job is as slow as its slowest rank
+    ms, e2e_max = ncd.max_over_ranks([ms, e2e[0] if e2e else 0.0], dev)
+    if e2e:
+        e2e = (e2e_max,) + e2e[1:]
 
     if rank == 0:
         ms_per_step = ms / args.steps
