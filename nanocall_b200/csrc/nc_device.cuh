@@ -73,6 +73,35 @@ __device__ __forceinline__ float emission(const StateParams& p, float x, float y
     return __fadd_rn(ln, li);
 }
 
+
+// The Viterbi kernel's form of the same emission, one multiply and one add shorter per state.  Multiplying by
+// 2 or 0.5 commutes exactly with IEEE rounding (no over/underflow at these magnitudes), so with
+//   ah = RN((x-mu)/sg)/2  (= div_rn with divisor 2*sg and reciprocal rsg/2),   q = RN(ah*ah) = RN(a*a)/4
+//   RN(RN(log_2pi + RN(a*a)) * 0.5)           == RN(q*2 + log_2pi/2)                 -- one FMA, 2q exact
+//   RN(RN(RN(c1 - ly3) - u) * 0.5)            == RN(RN(c1/2 - ly3/2) - u/2),  u/2 = div_rn(lam*b*b, 2y, ry/2)
+// every intermediate is the reference's value scaled by an exact power of two; the result has the same bits.
+struct StateParamsH
+{
+    float mu, sg2, rsgh, nls, eta, reta, lam, c1h;
+};
+__device__ __forceinline__ StateParamsH halve(const StateParams& p)
+{
+    StateParamsH h;
+    h.mu = p.mu; h.sg2 = __fadd_rn(p.sg, p.sg); h.rsgh = __fmul_rn(p.rsg, 0.5f); h.nls = p.nls;
+    h.eta = p.eta; h.reta = p.reta; h.lam = p.lam; h.c1h = __fmul_rn(p.c1, 0.5f);
+    return h;
+}
+// y2 = 2y, ly3h = (3 log y)/2, ryh = RN(1/y)/2, hl2pi = log_2pi/2
+__device__ __forceinline__ float emission_h(const StateParamsH& p, float x, float y, float y2, float ly3h, float ryh, float hl2pi)
+{
+    float ah = div_rn(__fsub_rn(x, p.mu), p.sg2, p.rsgh);
+    float ln = __fsub_rn(p.nls, __fmaf_rn(__fmul_rn(ah, ah), 2.0f, hl2pi));
+    float b = div_rn(__fsub_rn(y, p.eta), p.eta, p.reta);
+    float uh = div_rn(__fmul_rn(__fmul_rn(p.lam, b), b), y2, ryh);
+    float li = __fsub_rn(__fsub_rn(p.c1h, ly3h), uh);
+    return __fadd_rn(ln, li);
+}
+
 // 6-bit overlap mask of an edge i -> j: bit 0 = (i == j), bit l = suffix(i, 6-l) == prefix(j, 6-l)
 // (the conditions State_Transitions::get_trans_prob tests, State_Transitions.hpp:128-141)
 __device__ __forceinline__ unsigned trans_mask(unsigned i, unsigned j)

@@ -35,11 +35,15 @@ constexpr int ALPHA_PAD = 16;          // bank swizzle: upper half of the column
 constexpr int TB_SPEC_DEPTH = 96;      // speculative look-back of the blocked traceback
 constexpr int TB_MIN_BLOCK = 64;
 
-__device__ __forceinline__ int phys(int j) { return j + ((j >> 11) << 4); }
+// physical slot of alpha[j]: (1) the upper half of the column is shifted by 16 floats so the two threads of a
+// group (two-step candidates bb 0..7 / 8..15) hit different banks; (2) bit 2 is flipped when bit 5 is set so the two
+// STS.128 a thread issues for its 8 states (32-byte lane stride) are conflict-free.
+__device__ __forceinline__ int phys(int j) { return (j ^ (((j >> 5) & 1) << 2)) + ((j >> 11) << 4); }
 
 struct __align__(16) Smem
 {
     float alpha[2][NC_N_STATES + ALPHA_PAD];
+    float ws[NC_N_STATES + ALPHA_PAD];   // self-loop log-weights of the current job, same slots as alpha
     float4 ev[2][CH];
     float red_v[THREADS / 32];
     int red_j[THREADS / 32];
@@ -47,11 +51,38 @@ struct __align__(16) Smem
     unsigned short tb_start[THREADS];
     unsigned job;
     int final_state;
+    unsigned long long col_bar;   // mbarrier: one phase per event column
 };
 
 // stage one chunk of events: x = mean - drift*start (Event.hpp:81), y = stdv (0 -> 0.01,
-// Event.hpp:39-42), 3*log_stdv, RN(1/y)
+// Event.hpp:39-42), (3*log_stdv)/2, RN(1/y)/2   (the halves are exact scalings, see emission_h)
 struct EvRegs { float mean, stdv, start, lstd; };
+
+// Split-phase CTA barrier on an mbarrier: one lane per warp arrives once the warp's alpha stores are done
+// (__syncwarp orders them before the release), everybody waits on the phase parity later.  Between arrive and
+// wait a warp runs the next event's emission, so a warp that finishes its recursion early keeps issuing useful
+// work instead of idling at a bar.sync while the slowest warp catches up.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NC_WAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NC_DONE;\n"
+        "bra NC_WAIT;\n"
+        "NC_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 __device__ __forceinline__ EvRegs ev_load(const VitArgs& a, unsigned long long off, unsigned i, unsigned n)
 {
@@ -70,7 +101,7 @@ __device__ __forceinline__ float4 ev_pack(const EvRegs& r, float drift)
 {
     float y = (r.stdv == 0.0f) ? 0.01f : r.stdv;
     float x = __fsub_rn(r.mean, __fmul_rn(drift, r.start));
-    return make_float4(x, y, __fmul_rn(3.0f, r.lstd), __frcp_rn(y));
+    return make_float4(x, y, __fmul_rn(0.5f, __fmul_rn(3.0f, r.lstd)), __fmul_rn(0.5f, __frcp_rn(y)));
 }
 
 } // namespace
@@ -87,6 +118,11 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_kernel(const VitArgs a
     const unsigned g = t >> 1;
     unsigned char* const bp = a.bp_pool + (size_t)blockIdx.x * a.slab_bytes;
     const float log_2pi = a.log_2pi;
+    const float hl2pi = __fmul_rn(0.5f, a.log_2pi);
+    if (t == 0) mbar_init(&sm.col_bar, THREADS / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    unsigned col_phase = 0;
 
     for (;;)
     {
@@ -100,8 +136,7 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_kernel(const VitArgs a
         const unsigned long long off = J.ev_off;
 
         // ---------------- prologue: scaled model constants and transition weights into registers
-        StateParams P[SPT];
-        float ws[SPT];
+        StateParamsH P[SPT];
         {
             const float* M = a.models + (size_t)J.model * MODEL_FLOATS;
             float lm[SPT], ls[SPT], sdm[SPT], sdl[SPT], lls[SPT], lsl[SPT];
@@ -118,8 +153,8 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_kernel(const VitArgs a
 #pragma unroll
             for (int k = 0; k < SPT; ++k)
             {
-                P[k] = scale_state(lm[k], ls[k], sdm[k], sdl[k], lls[k], lsl[k], J, log_2pi);
-                ws[k] = J.lut[trans_mask(j0 + k, j0 + k)];
+                P[k] = halve(scale_state(lm[k], ls[k], sdm[k], sdl[k], lls[k], lsl[k], J, log_2pi));
+                sm.ws[phys(j0 + k)] = J.lut[trans_mask(j0 + k, j0 + k)];
             }
         }
         // two-step weight of group g: mask bits 2..5 (bit 2 always set); one-step weight of h: bits 1..5
@@ -136,12 +171,21 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_kernel(const VitArgs a
             const float4 E = sm.ev[0][0];
 #pragma unroll
             for (int k = 0; k < SPT; ++k)
-                a_own[k] = __fsub_rn(emission(P[k], E.x, E.y, E.z, E.w, log_2pi), a.log_n_states);
+                a_own[k] = __fsub_rn(emission_h(P[k], E.x, E.y, __fadd_rn(E.y, E.y), E.z, E.w, hl2pi), a.log_n_states);
             float* A = sm.alpha[0];
             *reinterpret_cast< float4* >(A + phys(j0)) = make_float4(a_own[0], a_own[1], a_own[2], a_own[3]);
             *reinterpret_cast< float4* >(A + phys(j0 + 4)) = make_float4(a_own[4], a_own[5], a_own[6], a_own[7]);
         }
         __syncthreads();
+        // emission of event 1, computed ahead: inside the loop the emission of event i+1 is issued next to the
+        // max-plus recursion of event i (independent work: the FP pipes run it while the ALU pipe does compare/select)
+        float e_cur[SPT];
+        {
+            const float4 E = sm.ev[0][1 & (CH - 1)];
+            const float y2 = __fadd_rn(E.y, E.y);
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) e_cur[k] = emission_h(P[k], E.x, E.y, y2, E.z, E.w, hl2pi);
+        }
 
         // ---------------- columns 1..n-1 (Viterbi.hpp:72-96)
         const int half = t & 1;
@@ -156,18 +200,30 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_kernel(const VitArgs a
             if (ic == 1 && t < CH) pre = ev_load(a, off, (i - 1) + CH + t, n);
             if (ic == 17 && t < CH) sm.ev[(((i - 1) / CH) + 1) & 1][t] = ev_pack(pre, J.drift);
 
-            const float4 E = sm.ev[(i / CH) & 1][ic];
+            const float4 E = sm.ev[((i + 1) / CH) & 1][(i + 1) & (CH - 1)];  // event i+1 (staged >= 1 barrier ago)
+            float ws[SPT];
+            *reinterpret_cast< float4* >(ws) = *reinterpret_cast< const float4* >(sm.ws + phys(j0));
+            *reinterpret_cast< float4* >(ws + 4) = *reinterpret_cast< const float4* >(sm.ws + phys(j0 + 4));
             const float* A = sm.alpha[cur];
+            const float y2 = __fadd_rn(E.y, E.y);
 
             // two-step candidates: 8 of the group's 16, ascending bb, strict '>'
-            float v2 = NC_NEG_INF;
-            int bb = 0;
+            // (tournament instead of a linear scan: the right operand wins only if strictly greater, so the lowest
+            //  index still wins ties, and the dependent chain is 3 compares deep instead of 8)
+            float c2[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-            {
-                float v = __fadd_rn(w2, A[two_off + (k << 8)]);
-                if (v > v2) { v2 = v; bb = k; }
-            }
+            for (int k = 0; k < 8; ++k) c2[k] = __fadd_rn(w2, A[two_off + (k << 8)]);
+            float m01 = c2[0], m23 = c2[2], m45 = c2[4], m67 = c2[6];
+            int i01 = 0, i23 = 2, i45 = 4, i67 = 6;
+            if (c2[1] > m01) { m01 = c2[1]; i01 = 1; }
+            if (c2[3] > m23) { m23 = c2[3]; i23 = 3; }
+            if (c2[5] > m45) { m45 = c2[5]; i45 = 5; }
+            if (c2[7] > m67) { m67 = c2[7]; i67 = 7; }
+            if (m23 > m01) { m01 = m23; i01 = i23; }
+            if (m67 > m45) { m45 = m67; i45 = i67; }
+            float v2 = m01;
+            int bb = i01;
+            if (m45 > v2) { v2 = m45; bb = i45; }
             bb += 8 * half;
             {
                 float ov = __shfl_xor_sync(0xffffffffu, v2, 1);
@@ -180,16 +236,26 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_kernel(const VitArgs a
             const int p2 = (bb << 8) | (int)g;
 
             // one-step candidates for h = 2t and 2t+1: ascending b, strict '>'
-            float v1[2] = { NC_NEG_INF, NC_NEG_INF };
-            int b1[2] = { 0, 0 };
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
+            float v1[2];
+            int b1[2];
             {
-                float2 o = *reinterpret_cast< const float2* >(A + phys((b << 10) + one_off));
-                float va = __fadd_rn(w1[0], o.x);
-                float vb = __fadd_rn(w1[1], o.y);
-                if (va > v1[0]) { v1[0] = va; b1[0] = b; }
-                if (vb > v1[1]) { v1[1] = vb; b1[1] = b; }
+                float ca[4], cb[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                {
+                    float2 o = *reinterpret_cast< const float2* >(A + phys((b << 10) + one_off));
+                    ca[b] = __fadd_rn(w1[0], o.x);
+                    cb[b] = __fadd_rn(w1[1], o.y);
+                }
+                float xa = ca[0], ya = ca[2], xb = cb[0], yb = cb[2];
+                int ia = 0, ja = 2, ib = 0, jb = 2;
+                if (ca[1] > xa) { xa = ca[1]; ia = 1; }
+                if (ca[3] > ya) { ya = ca[3]; ja = 3; }
+                if (cb[1] > xb) { xb = cb[1]; ib = 1; }
+                if (cb[3] > yb) { yb = cb[3]; jb = 3; }
+                if (ya > xa) { xa = ya; ia = ja; }
+                if (yb > xb) { xb = yb; ib = jb; }
+                v1[0] = xa; b1[0] = ia; v1[1] = xb; b1[1] = ib;
             }
             // merge two-step and one-step per h; equal values -> lower predecessor index
             float v12[2];
@@ -198,26 +264,35 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_kernel(const VitArgs a
             for (int hh = 0; hh < 2; ++hh)
             {
                 int p1 = (b1[hh] << 10) | (2 * t + hh);
-                bool take1 = (v1[hh] > v2) || (v1[hh] == v2 && p1 < p2);
+                bool take1 = (v1[hh] > v2) | ((v1[hh] == v2) & (p1 < p2));
                 v12[hh] = take1 ? v1[hh] : v2;
                 p12[hh] = take1 ? p1 : p2;
                 c12[hh] = take1 ? (16 + b1[hh]) : bb;
             }
-            // self candidate, emission, new alpha, backpointer code
+            // self candidate, emission, new alpha, backpointer code.  The 4 codes of an h-group start as the group's
+            // code replicated into every byte; a state whose self loop wins gets its byte replaced by 20 through a
+            // byte mask, so packing costs one select per state and three logic ops per word.
             float a_new[SPT];
-            unsigned code_lo = 0, code_hi = 0;
+            unsigned code_w[2];
 #pragma unroll
-            for (int k = 0; k < SPT; ++k)
+            for (int hh = 0; hh < 2; ++hh)
             {
-                const int hh = k >> 2;
-                float vs = __fadd_rn(ws[k], a_own[k]);
-                bool takes = (vs > v12[hh]) || (vs == v12[hh] && (int)(j0 + k) < p12[hh]);
-                float best = takes ? vs : v12[hh];
-                unsigned code = takes ? 20u : (unsigned)c12[hh];
-                a_new[k] = __fadd_rn(best, emission(P[k], E.x, E.y, E.z, E.w, log_2pi));
-                if (k < 4) code_lo |= code << (8 * k);
-                else code_hi |= code << (8 * (k - 4));
+                unsigned m = 0;
+                const int tie = p12[hh] - (int)j0 - 4 * hh;  // state kk of the group wins a tie iff kk < tie
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                {
+                    const int k = 4 * hh + kk;
+                    float vs = __fadd_rn(ws[k], a_own[k]);
+                    bool takes = (vs > v12[hh]) | ((vs == v12[hh]) & (kk < tie));
+                    float best = takes ? vs : v12[hh];
+                    m |= takes ? (0xffu << (8 * kk)) : 0u;
+                    a_new[k] = __fadd_rn(best, e_cur[k]);
+                }
+                const unsigned base = (unsigned)c12[hh] * 0x01010101u;
+                code_w[hh] = (base & ~m) | (0x14141414u & m);
             }
+            const unsigned code_lo = code_w[0], code_hi = code_w[1];
             float* An = sm.alpha[cur ^ 1];
             *reinterpret_cast< float4* >(An + phys(j0)) = make_float4(a_new[0], a_new[1], a_new[2], a_new[3]);
             *reinterpret_cast< float4* >(An + phys(j0 + 4)) = make_float4(a_new[4], a_new[5], a_new[6], a_new[7]);
@@ -226,7 +301,13 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_kernel(const VitArgs a
 #pragma unroll
             for (int k = 0; k < SPT; ++k) a_own[k] = a_new[k];
             cur ^= 1;
-            __syncthreads();
+            // column i is published: arrive now, wait after the next event's emission
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.col_bar);
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) e_cur[k] = emission_h(P[k], E.x, E.y, y2, E.z, E.w, hl2pi);
+            mbar_wait(&sm.col_bar, col_phase & 1u);
+            ++col_phase;
         }
 
         // ---------------- fill_state_seq: argmax over the last column, strict '>' ascending j (Viterbi.hpp:123-133)
