@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="0 = 2 per host thread")
+    ap.add_argument("--vit-mode", default="auto", choices=["auto", "backpointer"],
+                    help="auto = alpha-column kernel where the columns fit the pool; backpointer = long-read kernel only")
     return ap.parse_args()
 
 
@@ -192,6 +194,9 @@ def main():
     ctx = api.Context(local_rank)
     mid = ctx.register_model(table, 0)
     info = ctx.device_info()
+    if args.vit_mode == "backpointer":
+        from nanocall_b200 import _lib as L
+        ctx.set_viterbi_mode(L.NC_VIT_BACKPOINTER)
 
     # pinned host copies (e2e) and device-resident copies (value)
     host = {k: torch.from_numpy(v).pin_memory() for k, v in
@@ -223,8 +228,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     path = None
+    launches = 0
     for _ in range(args.steps):
         path = step_device()
+        launches += ctx.last_launches()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -282,7 +289,7 @@ def main():
                        "l2": "inputs (1.2 GB events per 1e8 events + 41 MB backpointers per read) larger than L2",
                        "device": info["name"], "n_sms": info["n_sms"]},
             "clocks": clocks,
-            "gpu_launches": args.steps,
+            "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind,
                          "kernel": "viterbi_kernel", "algorithmic_bytes_per_event": HBM_BYTES_PER_EVENT},

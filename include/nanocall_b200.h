@@ -53,6 +53,13 @@ void* nc_ctx_stream(nc_ctx* ctx);
 int nc_ctx_sync(nc_ctx* ctx);
 /* device time (CUDA events on the context's stream) of the most recent hot-path kernel launch, ms */
 float nc_ctx_last_kernel_ms(nc_ctx* ctx);
+/* kernels launched by the most recent nc_viterbi_packed call (bench.py's gpu_launches) */
+int nc_ctx_last_launches(nc_ctx* ctx);
+/* Viterbi kernel choice: NC_VIT_AUTO = alpha-column kernel for every job whose columns fit a pool slab (16 KiB per
+ * event), backpointer kernel (4 KiB per event) for longer jobs; NC_VIT_BACKPOINTER = backpointer kernel only.
+ * Both produce the reference's bits; the switch exists for A/B measurements and tests. */
+typedef enum { NC_VIT_AUTO = 0, NC_VIT_BACKPOINTER = 2 } nc_vit_mode;
+int nc_ctx_set_viterbi_mode(nc_ctx* ctx, int mode);
 /* number of SMs / name of the device, for reports */
 int nc_ctx_device_info(nc_ctx* ctx, int* n_sms, size_t* total_mem, char* name, int name_cap);
 

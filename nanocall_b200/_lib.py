@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libnanocall_b200.so")
 
 NC_OK, NC_ERR_ARG, NC_ERR_CUDA, NC_ERR_NOMEM, NC_ERR_STATE = 0, -1, -2, -3, -4
 NC_MEM_HOST, NC_MEM_DEVICE = 0, 1
+NC_VIT_AUTO, NC_VIT_BACKPOINTER = 0, 2
 
 
 class PmParams(C.Structure):
@@ -52,6 +53,8 @@ SYMBOLS = {
     "nc_ctx_stream": (_vp, [_vp]),
     "nc_ctx_sync": (C.c_int, [_vp]),
     "nc_ctx_last_kernel_ms": (C.c_float, [_vp]),
+    "nc_ctx_last_launches": (C.c_int, [_vp]),
+    "nc_ctx_set_viterbi_mode": (C.c_int, [_vp, C.c_int]),
     "nc_ctx_device_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.c_char_p, C.c_int]),
     "nc_model_register": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     "nc_model_stats": (C.c_int, [_vp, C.c_int, C.POINTER(_f), C.POINTER(_f)]),

@@ -81,6 +81,13 @@ class Context:
     def last_kernel_ms(self):
         return float(self.lib.nc_ctx_last_kernel_ms(self.h))
 
+    def last_launches(self):
+        return int(self.lib.nc_ctx_last_launches(self.h))
+
+    def set_viterbi_mode(self, mode):
+        """L.NC_VIT_AUTO (alpha-column kernel where it fits) or L.NC_VIT_BACKPOINTER."""
+        self._check(self.lib.nc_ctx_set_viterbi_mode(self.h, int(mode)))
+
     def device_info(self):
         n, mem, name = C.c_int(), C.c_size_t(), C.create_string_buffer(256)
         self._check(self.lib.nc_ctx_device_info(self.h, C.byref(n), C.byref(mem), name, 256))

@@ -52,6 +52,9 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
     if ((e = cudaFuncSetAttribute(nc::viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)nc::viterbi_smem_bytes())) != cudaSuccess)
         return fail("cudaFuncSetAttribute(viterbi_kernel)", e);
+    if ((e = cudaFuncSetAttribute(nc::viterbi_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)nc::viterbi_alpha_smem_bytes())) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(viterbi_alpha_kernel)", e);
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
     unsigned hc = std::thread::hardware_concurrency();
     ctx->host_threads = hc ? std::min(hc, 32u) : 4u;
@@ -82,6 +85,16 @@ const char* nc_last_error(const nc_ctx* ctx) { return ctx ? ctx->err.c_str() : g
 void* nc_ctx_stream(nc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 float nc_ctx_last_kernel_ms(nc_ctx* ctx) { return ctx ? ctx->last_kernel_ms : -1.f; }
+
+int nc_ctx_last_launches(nc_ctx* ctx) { return ctx ? ctx->last_launches : -1; }
+
+int nc_ctx_set_viterbi_mode(nc_ctx* ctx, int mode)
+{
+    if (!ctx) return NC_ERR_ARG;
+    if (mode != NC_VIT_AUTO && mode != NC_VIT_BACKPOINTER) NC_FAIL(ctx, NC_ERR_ARG, "nc_ctx_set_viterbi_mode: bad mode %d", mode);
+    ctx->vit_mode = mode;
+    return NC_OK;
+}
 
 int nc_ctx_sync(nc_ctx* ctx)
 {
@@ -185,35 +198,64 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
             max_len = std::max(max_len, J.n_events);
         }
     }
+    // ---- which kernel decodes which job.  The alpha-column kernel is the fast path; it needs 16 KiB of scratch per
+    // event of every job in flight (one slab per CTA), the backpointer kernel 4 KiB.  With the pool cut into one slab
+    // per CTA, jobs that fit a slab as alpha columns take the fast path, longer ones the backpointer kernel.  A call
+    // that wants no states (candidate ranking by path probability) needs no scratch at all.
+    const bool want_path = states != nullptr || moves != nullptr;
+    const size_t n_sms = (size_t)ctx->prop.multiProcessorCount;
+    const size_t ctas_wanted = std::min< size_t >(n_jobs, n_sms);
+    const size_t a_col = (size_t)NC_N_STATES * sizeof(float), b_col = (size_t)NC_N_STATES;
+    uint32_t alpha_max_len = 0xffffffffu;
+    if (want_path)
+        alpha_max_len = (uint32_t)std::min< size_t >((ctx->bp_bytes / ctas_wanted) / a_col, 0xffffffffu);
+    if (ctx->vit_mode == 2) alpha_max_len = 0;   // forced backpointer form (tests, A/B measurements)
     std::vector< unsigned > order(n_jobs);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return jobs[a].n_events > jobs[b].n_events; });
-
-    const size_t slab = (size_t)max_len * NC_N_STATES;
-    size_t max_ctas = ctx->bp_bytes / slab;
-    if (max_ctas == 0)
-        NC_FAIL(ctx, NC_ERR_NOMEM, "nc_viterbi_packed: a %u-event job needs %zu backpointer bytes, pool has %zu",
-                max_len, slab, ctx->bp_bytes);
-    unsigned grid = (unsigned)std::min< size_t >(std::min< size_t >(n_jobs, (size_t)ctx->prop.multiProcessorCount), max_ctas);
+    // order = [long jobs (backpointer form) | the rest (alpha form)], each longest first
+    uint32_t n_long = 0;
+    while (n_long < n_jobs && jobs[order[n_long]].n_events > alpha_max_len) ++n_long;
+    const uint32_t n_short = n_jobs - n_long;
+    unsigned grid_b = 0, grid_a = 0;
+    size_t slab_b = 0, slab_a = 0;
+    if (n_long)
+    {
+        slab_b = (size_t)max_len * b_col;
+        const size_t fit = ctx->bp_bytes / slab_b;
+        if (fit == 0)
+            NC_FAIL(ctx, NC_ERR_NOMEM, "nc_viterbi_packed: a %u-event job needs %zu backpointer bytes, pool has %zu",
+                    max_len, slab_b, ctx->bp_bytes);
+        grid_b = (unsigned)std::min< size_t >(std::min< size_t >(n_long, n_sms), fit);
+    }
+    if (n_short)
+    {
+        grid_a = (unsigned)std::min< size_t >(n_short, n_sms);
+        if (want_path)
+        {
+            slab_a = (size_t)jobs[order[n_long]].n_events * a_col;
+            grid_a = (unsigned)std::min< size_t >(grid_a, ctx->bp_bytes / slab_a);
+        }
+    }
 
     int rc;
     if ((rc = dev_reserve(ctx, ctx->jobs, n_jobs * sizeof(nc::DevJob))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->order, n_jobs * sizeof(unsigned))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->counter, sizeof(unsigned))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->counter, 2 * sizeof(unsigned))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->path, n_jobs * sizeof(float))) != NC_OK) return rc;
     cudaStream_t s = ctx->stream;
     NC_CUDA(ctx, cudaMemcpyAsync(ctx->jobs.p, jobs.data(), n_jobs * sizeof(nc::DevJob), cudaMemcpyHostToDevice, s));
     NC_CUDA(ctx, cudaMemcpyAsync(ctx->order.p, order.data(), n_jobs * sizeof(unsigned), cudaMemcpyHostToDevice, s));
-    NC_CUDA(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), s));
+    NC_CUDA(ctx, cudaMemsetAsync(ctx->counter.p, 0, 2 * sizeof(unsigned), s));
 
     nc::VitArgs a;
     a.jobs = (const nc::DevJob*)ctx->jobs.p;
     a.order = (const unsigned*)ctx->order.p;
-    a.n_jobs = n_jobs;
+    a.n_jobs = n_long;
     a.next_job = (unsigned*)ctx->counter.p;
     a.models = ctx->d_models;
     a.bp_pool = ctx->d_bp;
-    a.slab_bytes = slab;
+    a.slab_bytes = slab_b;
     a.path_logprob = (float*)ctx->path.p;
     a.log_2pi = (float)std::log(2.0 * M_PI);
     a.log_n_states = std::log((float)NC_N_STATES);
@@ -258,8 +300,24 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     }
 
     NC_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
-    nc::viterbi_kernel<<< grid, nc::VIT_THREADS, nc::viterbi_smem_bytes(), s >>>(a);
-    NC_CUDA(ctx, cudaGetLastError());
+    ctx->last_launches = 0;
+    if (n_long)
+    {
+        nc::viterbi_kernel<<< grid_b, nc::VIT_THREADS, nc::viterbi_smem_bytes(), s >>>(a);
+        NC_CUDA(ctx, cudaGetLastError());
+        ++ctx->last_launches;
+    }
+    if (n_short)
+    {
+        nc::VitArgs b = a;
+        b.order = a.order + n_long;
+        b.n_jobs = n_short;
+        b.next_job = a.next_job + 1;
+        b.slab_bytes = slab_a;
+        nc::viterbi_alpha_kernel<<< grid_a, nc::VIT_THREADS, nc::viterbi_alpha_smem_bytes(), s >>>(b);
+        NC_CUDA(ctx, cudaGetLastError());
+        ++ctx->last_launches;
+    }
     NC_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
 
     NC_CUDA(ctx, cudaMemcpyAsync(path_logprob, ctx->path.p, n_jobs * sizeof(float), cudaMemcpyDeviceToHost, s));

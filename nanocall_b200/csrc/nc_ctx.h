@@ -38,6 +38,8 @@ struct nc_ctx
     unsigned host_threads = 1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_kernel_ms = 0.f;
+    int last_launches = 0;        // kernels launched by the most recent nc_viterbi_packed
+    int vit_mode = 0;             // 0 = auto, 2 = backpointer kernel only (nc_ctx_set_viterbi_mode)
 };
 
 #define NC_FAIL(ctx, code, ...)                                        \

@@ -20,7 +20,8 @@ struct VitArgs
     const float* stdv;
     const float* start;
     const float* log_stdv;
-    unsigned char* bp_pool;     // gridDim.x slabs of slab_bytes
+    unsigned char* bp_pool;     // gridDim.x slabs of slab_bytes: backpointers (viterbi_kernel, 4096 B/event) or
+                                // alpha columns (viterbi_alpha_kernel, 16384 B/event)
     size_t slab_bytes;
     float* path_logprob;        // n_jobs
     unsigned short* states;     // packed like the events, may be null
@@ -29,8 +30,10 @@ struct VitArgs
     float log_n_states;         // logf(4096.f)      (Viterbi.hpp:51)
 };
 
-__global__ void viterbi_kernel(const VitArgs a);
+__global__ void viterbi_kernel(const VitArgs a);        // backpointer form (long reads: 4 KiB/event of scratch)
 size_t viterbi_smem_bytes();
+__global__ void viterbi_alpha_kernel(const VitArgs a);  // alpha-column form (fast path: 16 KiB/event of scratch)
+size_t viterbi_alpha_smem_bytes();
 
 // ---- Forward/Backward + trainer statistics
 enum { FB_EV_TILE = 16 };

@@ -13,6 +13,16 @@ R73C1 = "r73.c.p1.006.ont.model"
 R73C2 = "r73.c.p2.006.ont.model"
 
 
+@pytest.fixture(autouse=True, params=["alpha", "backpointer"])
+def vit_mode(request, ctx):
+    """Every test runs against both Viterbi kernels: the alpha-column kernel (fast path, arg max evaluated in the
+    traceback) and the backpointer kernel (long-read path); both must give the reference's bits."""
+    from nanocall_b200 import _lib as L
+    ctx.set_viterbi_mode(L.NC_VIT_BACKPOINTER if request.param == "backpointer" else L.NC_VIT_AUTO)
+    yield request.param
+    ctx.set_viterbi_mode(L.NC_VIT_AUTO)
+
+
 def _bits(x):
     return np.asarray(x, np.float32).view(np.uint32)
 
@@ -168,3 +178,39 @@ def test_host_supplied_log_stdv_equals_device_logf(ctx, port, models):
     b = ctx.viterbi(batch["ev_off"], batch["mean"], batch["stdv"], batch["start"], mid, log_stdv=lstd)
     assert np.array_equal(_bits(a["path_logprob"]), _bits(b["path_logprob"]))
     assert np.array_equal(a["states"], b["states"])
+
+
+def test_mixed_dispatch_small_pool(port, models, vit_mode):
+    """A pool too small for the long job's alpha columns: that job takes the backpointer kernel, the short ones the
+    alpha kernel, in the same call (two launches); outputs identical to the oracle either way."""
+    if vit_mode != "alpha":
+        pytest.skip("dispatch test runs once")
+    table = models[R73T]["table"]
+    lengths = [3000, 40, 900, 2500, 200, 100]
+    # 6 CTAs wanted; 3000 events need 12.3 MB of backpointers, a slab of pool/6 = 16 MiB holds 1024 alpha columns
+    c = api.Context(0, bp_pool_bytes=96 << 20)
+    try:
+        mid = c.register_model(table, 0)
+        batch = synth.make_batch(51, table, lengths)
+        _check_batch(c, port, table, mid, batch, None, None)
+        assert c.last_launches() == 2
+    finally:
+        c.close()
+
+
+def test_path_probability_only_needs_no_scratch(port, models, vit_mode):
+    """states=NULL, moves=NULL (candidate ranking): no columns are stored, so even a tiny pool serves long jobs."""
+    if vit_mode != "alpha":
+        pytest.skip("runs once")
+    table = models[R73T]["table"]
+    c = api.Context(0, bp_pool_bytes=1 << 20)
+    try:
+        mid = c.register_model(table, 0)
+        batch = synth.make_batch(52, table, [5000, 300])
+        out = c.viterbi(batch["ev_off"], batch["mean"], batch["stdv"], batch["start"], mid,
+                        want_states=False, want_moves=False)
+        exp = port.viterbi_batch(table, batch["ev_off"], batch["mean"], batch["stdv"], batch["start"],
+                                 api._pm_array(None, 2), api._st_array(None, 2), n_threads=8)
+        assert np.array_equal(_bits(out["path_logprob"]), _bits(exp["path_prob"]))
+    finally:
+        c.close()
