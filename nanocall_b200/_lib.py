@@ -7,7 +7,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnanocall_b200.so")
+# NC_LIB_PATH: load another build of the same library (kernel A/B experiments); never a different implementation
+LIB_PATH = os.environ.get("NC_LIB_PATH") or os.path.join(_HERE, "libnanocall_b200.so")
 
 NC_OK, NC_ERR_ARG, NC_ERR_CUDA, NC_ERR_NOMEM, NC_ERR_STATE = 0, -1, -2, -3, -4
 NC_MEM_HOST, NC_MEM_DEVICE = 0, 1

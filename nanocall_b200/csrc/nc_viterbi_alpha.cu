@@ -19,8 +19,18 @@
 // from those bits with the reference's rule: first maximum in ascending predecessor order (strict '>').
 //
 // Mapping: as viterbi_kernel -- one persistent CTA of 512 threads per SM, thread t owns states 8t..8t+7, previous
-// column double-buffered in shared memory, emission of event i+1 computed behind the split-phase column barrier.
+// column double-buffered in shared memory, one mbarrier phase per column.
+//
+// What binds (tools/ubench/emis.cu, profiles/): the fused emission alone keeps the FMA pipe busy ~730 cycles per
+// column and SM sub-partition, everything else must hide behind it.  So (1) the loop body carries no integer
+// arithmetic on the FMA pipe (IMAD runs there at half rate): every shared-memory access is `base register +
+// immediate`, the loop is unrolled by two so buffer and barrier parity are compile-time constants; (2) the emission
+// is split: state pairs 2,3 of event i are computed next to the predecessor loads / max tree / shuffle of column i
+// (filling that chain's latency bubbles), pairs 0,1 of event i+1 between the barrier arrive and the barrier wait
+// (filling the barrier bubble); (3) the emission runs as packed FADD2/FMUL2/FFMA2 to halve its issue slots.
 #include "nc_vit_common.cuh"
+
+#include <type_traits>
 
 namespace nc {
 
@@ -28,10 +38,102 @@ using namespace vit;
 
 namespace {
 
+
+__device__ __forceinline__ void st_cs_v8(float* p, const float (&v)[8])
+{
+    // one 256-bit streaming store: every lane writes a full 32-byte sector, a warp 1 KiB contiguous
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
+
+// ---- packed binary32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest operations per issue slot.
+// The FMA pipe still spends two cycles on them; what they save is issue bandwidth, which the emission (19 FP
+// operations per state and event) would otherwise monopolise.  Element-wise they are the scalar operations, so the
+// emission keeps the reference's bits (tests/test_viterbi_gpu.py runs every case through this kernel).
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo_of(f2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi_of(f2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// Emission constants of two adjacent states, subtrahends stored negated so every step is an add / mul / fma
+// (RN(a - b) == RN(a + (-b)) and RN(-(x)) == -RN(x): same bits as emission_h in nc_device.cuh).
+// Event operands: X = x, Y = y, Y2 = 2y, NLY = -(3 log y)/2, NRY = -RN(1/y)/2, each broadcast to both halves
+struct EvPairs { f2 X, Y, Y2, NLY, NRY; };
+// log_pr_corrected_emission for two states (Pore_Model.hpp:24-40,145-149), step for step emission_h:
+//   ah = RN((x-mu)/(2 sg)) by Markstein division;  ln = nls - (2 ah^2 + log_2pi/2)
+//   b  = RN((y-eta)/eta);  uh = RN(lam b b / (2y));  li = (c1/2 - (3 log y)/2) - uh;   e = ln + li
+// nls and c1h are passed separately: the kernel keeps them in shared memory to make room in the register file.
+struct PairRegs { f2 nmu, nsg2, rsgh, neta, reta, lam; };
+__device__ __forceinline__ f2 emission2(const PairRegs& p, f2 nls, f2 c1h, const EvPairs& e, f2 m2, f2 nhl2pi)
+{
+    const f2 t1 = add2(e.X, p.nmu);
+    const f2 q0 = mul2(t1, p.rsgh);
+    const f2 r = fma2(q0, p.nsg2, t1);
+    const f2 ah = fma2(r, p.rsgh, q0);
+    const f2 ns = fma2(mul2(ah, ah), m2, nhl2pi);     // -(2 ah^2 + log_2pi/2)
+    const f2 ln = add2(nls, ns);
+    const f2 t2 = add2(e.Y, p.neta);
+    const f2 p0 = mul2(t2, p.reta);
+    const f2 r2 = fma2(p0, p.neta, t2);
+    const f2 b = fma2(r2, p.reta, p0);
+    const f2 l2 = mul2(mul2(p.lam, b), b);
+    const f2 nq = mul2(l2, e.NRY);                    // -RN(l2 * ry/2)
+    const f2 r3 = fma2(nq, e.Y2, l2);
+    const f2 nuh = fma2(r3, e.NRY, nq);               // -uh
+    const f2 li = add2(add2(c1h, e.NLY), nuh);
+    return add2(ln, li);
+}
+// event as staged for this kernel: {x, y, -(3 log y)/2, -RN(1/y)/2}
+__device__ __forceinline__ float4 ev_slot(const float4& p) { return make_float4(p.x, p.y, -p.z, -p.w); }
+__device__ __forceinline__ EvPairs ev_pairs(const float4& s)
+{
+    EvPairs e;
+    const float y2 = __fadd_rn(s.y, s.y);
+    e.X = pk(s.x, s.x); e.Y = pk(s.y, s.y); e.Y2 = pk(y2, y2); e.NLY = pk(s.z, s.z); e.NRY = pk(s.w, s.w);
+    return e;
+}
+// shared-memory access by 32-bit shared address: one base register + immediate offset in SASS, no generic-address
+// arithmetic.  volatile: ordered against the barrier asm statements.
+__device__ __forceinline__ float lds32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds64(unsigned a) { float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ f2 lds64p(unsigned a) { f2 v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds128(unsigned a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_if(unsigned bar, unsigned pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\n@p mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n}" ::"r"(bar), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NC_WAITA:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NC_DONEA;\n"
+        "bra NC_WAITA;\n"
+        "NC_DONEA:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
 struct __align__(16) SmemA
 {
     float alpha[2][NC_N_STATES + ALPHA_PAD];
-    float4 ev[2][CH];
+    float4 ev[2 * CH];             // two chunks of staged events (slot = event index & 255)
+    f2 prm[2][SPT / 2][THREADS];   // nls / c1h of every state pair, slot [.][pair][thread]: conflict-free LDS.64
     float lut[64];                 // transition log-weights of the current job (traceback)
     float red_v[THREADS / 32];
     int red_j[THREADS / 32];
@@ -41,14 +143,6 @@ struct __align__(16) SmemA
     int final_state;
     unsigned long long col_bar;    // mbarrier: one phase per event column
 };
-
-__device__ __forceinline__ void st_cs_v8(float* p, const float (&v)[8])
-{
-    // one 256-bit streaming store: every lane writes a full 32-byte sector, a warp 1 KiB contiguous
-    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
-}
 
 // One traceback step: the predecessor of state s, given the alpha column of the previous event.
 // Candidates as in the forward pass (two-step class weight w2(g), one-step class weight w1(h), exact self weight);
@@ -105,10 +199,10 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
     const bool keep = a.states != nullptr;   // path probability only: nothing to trace back, nothing stored
     const float log_2pi = a.log_2pi;
     const float hl2pi = __fmul_rn(0.5f, a.log_2pi);
+    const unsigned bar = smem_u32(&sm.col_bar);
     if (t == 0) mbar_init(&sm.col_bar, THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    unsigned col_phase = 0;
 
     for (;;)
     {
@@ -121,9 +215,11 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
         const unsigned n = J.n_events;
         const unsigned long long off = J.ev_off;
 
-        // ---------------- prologue: scaled model constants and transition weights into registers
-        StateParamsH P[SPT];
-        float ws[SPT];
+        // ---------------- prologue: scaled model constants (as state pairs) and transition weights
+        PairRegs P[SPT / 2];
+        f2 ws[SPT / 2];
+        const unsigned prm_nls = smem_u32(&sm.prm[0][0][t]), prm_c1h = smem_u32(&sm.prm[1][0][t]);
+        constexpr unsigned PRM_PAIR = THREADS * sizeof(f2);   // byte stride between the pairs of one thread
         {
             const float* M = a.models + (size_t)J.model * MODEL_FLOATS;
             float lm[SPT], ls[SPT], sdm[SPT], sdl[SPT], lls[SPT], lsl[SPT];
@@ -138,104 +234,148 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
                 *reinterpret_cast< float4* >(lsl + 4 * v) = __ldg(reinterpret_cast< const float4* >(M + 5 * NC_N_STATES + j0) + v);
             }
 #pragma unroll
-            for (int k = 0; k < SPT; ++k)
+            for (int k = 0; k < SPT; k += 2)
             {
-                P[k] = halve(scale_state(lm[k], ls[k], sdm[k], sdl[k], lls[k], lsl[k], J, log_2pi));
-                ws[k] = J.lut[trans_mask(j0 + k, j0 + k)];
+                const StateParamsH x = halve(scale_state(lm[k], ls[k], sdm[k], sdl[k], lls[k], lsl[k], J, log_2pi));
+                const StateParamsH y = halve(scale_state(lm[k + 1], ls[k + 1], sdm[k + 1], sdl[k + 1], lls[k + 1], lsl[k + 1], J, log_2pi));
+                PairRegs& p = P[k / 2];
+                p.nmu = pk(-x.mu, -y.mu); p.nsg2 = pk(-x.sg2, -y.sg2); p.rsgh = pk(x.rsgh, y.rsgh);
+                p.neta = pk(-x.eta, -y.eta); p.reta = pk(x.reta, y.reta); p.lam = pk(x.lam, y.lam);
+                sm.prm[0][k / 2][t] = pk(x.nls, y.nls);      // read back by this thread only
+                sm.prm[1][k / 2][t] = pk(x.c1h, y.c1h);
+                ws[k / 2] = pk(J.lut[trans_mask(j0 + k, j0 + k)], J.lut[trans_mask(j0 + k + 1, j0 + k + 1)]);
             }
             if (t < 64) sm.lut[t] = J.lut[t];
         }
         // two-step weight of group g: mask bits 2..5 (bit 2 always set); one-step weight of h: bits 1..5
         const float w2 = J.lut[trans_mask(g, j0) & 0x3cu];
-        float w1[2];
-        w1[0] = J.lut[trans_mask(2 * t, j0) & 0x3eu];
-        w1[1] = J.lut[trans_mask(2 * t + 1, j0 + 4) & 0x3eu];
+        const float w1a = J.lut[trans_mask(2 * t, j0) & 0x3eu];
+        const float w1b = J.lut[trans_mask(2 * t + 1, j0 + 4) & 0x3eu];
+        const f2 M2 = pk(-2.0f, -2.0f), NH = pk(-hl2pi, -hl2pi);
 
         // ---------------- first chunk of events, column 0 (Viterbi.hpp:57-67)
-        if (t < CH) sm.ev[0][t] = ev_pack(ev_load(a, off, t, n), J.drift);
+        if (t < CH) sm.ev[t] = ev_slot(ev_pack(ev_load(a, off, t, n), J.drift));
         __syncthreads();
-        float a_own[SPT];
+        f2 a_own[SPT / 2];
         {
-            const float4 E = sm.ev[0][0];
+            const EvPairs E = ev_pairs(sm.ev[0]);
+            const f2 nlog_n = pk(-a.log_n_states, -a.log_n_states);
+            float a0[SPT];
 #pragma unroll
-            for (int k = 0; k < SPT; ++k)
-                a_own[k] = __fsub_rn(emission_h(P[k], E.x, E.y, __fadd_rn(E.y, E.y), E.z, E.w, hl2pi), a.log_n_states);
+            for (int k = 0; k < SPT / 2; ++k)
+            {
+                a_own[k] = add2(emission2(P[k], sm.prm[0][k][t], sm.prm[1][k][t], E, M2, NH), nlog_n);
+                a0[2 * k] = lo_of(a_own[k]);
+                a0[2 * k + 1] = hi_of(a_own[k]);
+            }
             float* A = sm.alpha[0];
-            *reinterpret_cast< float4* >(A + phys(j0)) = make_float4(a_own[0], a_own[1], a_own[2], a_own[3]);
-            *reinterpret_cast< float4* >(A + phys(j0 + 4)) = make_float4(a_own[4], a_own[5], a_own[6], a_own[7]);
-            if (keep) st_cs_v8(acol + j0, a_own);
+            *reinterpret_cast< float4* >(A + phys(j0)) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+            *reinterpret_cast< float4* >(A + phys(j0 + 4)) = make_float4(a0[4], a0[5], a0[6], a0[7]);
+            if (keep) st_cs_v8(acol + j0, a0);
+        }
+        // emission of event 1 for state pairs 0,1: carried into the loop (the loop computes it one event ahead)
+        f2 e01[2];
+        {
+            const EvPairs E = ev_pairs(sm.ev[1]);
+            e01[0] = emission2(P[0], sm.prm[0][0][t], sm.prm[1][0][t], E, M2, NH);
+            e01[1] = emission2(P[1], sm.prm[0][1][t], sm.prm[1][1][t], E, M2, NH);
         }
         __syncthreads();
-        float e_cur[SPT];
-        {
-            const float4 E = sm.ev[0][1 & (CH - 1)];
-            const float y2 = __fadd_rn(E.y, E.y);
-#pragma unroll
-            for (int k = 0; k < SPT; ++k) e_cur[k] = emission_h(P[k], E.x, E.y, y2, E.z, E.w, hl2pi);
-        }
 
         // ---------------- columns 1..n-1 (Viterbi.hpp:72-96), max only
+        constexpr unsigned COL_BYTES = (NC_N_STATES + ALPHA_PAD) * sizeof(float);
+        const unsigned alpha0 = smem_u32(&sm.alpha[0][0]);
         const int half = t & 1;
-        const int two_off = phys(((8 * half) << 8) + (int)g);  // first of this thread's 8 two-step predecessors
-        const int one_off = 2 * t;                              // (b<<10) + 2t, b = 0..3
-        int cur = 0;
+        const unsigned two_b = alpha0 + 4u * (unsigned)phys(((8 * half) << 8) + (int)g);  // this thread's 8 two-step predecessors
+        const unsigned one_b = alpha0 + 4u * (unsigned)phys(2 * t);                        // + (b<<10) + ((b>>1)<<4) floats, b = 0..3
+        const unsigned wr_lo = alpha0 + 4u * (unsigned)phys(j0), wr_hi = alpha0 + 4u * (unsigned)phys(j0 + 4);
+        const unsigned ev_b = smem_u32(&sm.ev[0]);
         EvRegs pre = { 0.f, 1.f, 0.f, 0.f };
         float* gcol = acol + NC_N_STATES + j0;                  // this thread's 8 slots of column i
-        for (unsigned i = 1; i < n; ++i)
-        {
-            const unsigned ic = i & (CH - 1);
-            if (ic == 1 && t < CH) pre = ev_load(a, off, (i - 1) + CH + t, n);
-            if (ic == 17 && t < CH) sm.ev[(((i - 1) / CH) + 1) & 1][t] = ev_pack(pre, J.drift);
+        const unsigned lane0 = (lane == 0) ? 1u : 0u;
 
-            const float4 E = sm.ev[((i + 1) / CH) & 1][(i + 1) & (CH - 1)];  // event i+1 (staged >= 1 barrier ago)
-            const float* A = sm.alpha[cur];
-            const float y2 = __fadd_rn(E.y, E.y);
-
-            // two-step class: max over this thread's 8 of the group's 16 predecessors, the partner holds the rest
+        auto column = [&](auto cur_tag, const unsigned i) {
+            constexpr unsigned RD = decltype(cur_tag)::value * COL_BYTES;          // column i-1
+            constexpr unsigned WR = (1 - decltype(cur_tag)::value) * COL_BYTES;    // column i
+            if constexpr (decltype(cur_tag)::value == 0)   // i is odd in this half: the staging points are odd
+            {
+                const unsigned ic = i & (CH - 1);
+                if (ic == 1 && t < CH) pre = ev_load(a, off, (i - 1) + CH + t, n);
+                if (ic == 17 && t < CH) sm.ev[((((i - 1) / CH) + 1) & 1) * CH + t] = ev_slot(ev_pack(pre, J.drift));
+            }
+            // ---- part 1: column i-1 is complete.  Predecessor loads first, then the rest of this event's emission.
             float c2[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) c2[k] = A[two_off + (k << 8)];
-            float m2 = fmaxf(fmaxf(fmaxf(c2[0], c2[1]), fmaxf(c2[2], c2[3])), fmaxf(fmaxf(c2[4], c2[5]), fmaxf(c2[6], c2[7])));
-            m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 1));
-            const float v2 = __fadd_rn(w2, m2);
-
-            // one-step class for h = 2t and 2t+1
+            for (int k = 0; k < 8; ++k) c2[k] = lds32(two_b + RD + (k << 10));
             float2 o[4];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) o[b] = *reinterpret_cast< const float2* >(A + phys((b << 10) + one_off));
-            const float m1a = fmaxf(fmaxf(o[0].x, o[1].x), fmaxf(o[2].x, o[3].x));
-            const float m1b = fmaxf(fmaxf(o[0].y, o[1].y), fmaxf(o[2].y, o[3].y));
-            float v12[2];
-            v12[0] = fmaxf(__fadd_rn(w1[0], m1a), v2);
-            v12[1] = fmaxf(__fadd_rn(w1[1], m1b), v2);
-
-            // self candidate, emission
+            for (int b = 0; b < 4; ++b) o[b] = lds64(one_b + RD + (b << 12) + ((b >> 1) << 6));
+            const float4 ev_i = lds128(ev_b + ((i & (2 * CH - 1)) << 4));
+            f2 e23[2];
+            {
+                const EvPairs E = ev_pairs(ev_i);
+                e23[0] = emission2(P[2], lds64p(prm_nls + 2 * PRM_PAIR), lds64p(prm_c1h + 2 * PRM_PAIR), E, M2, NH);
+                e23[1] = emission2(P[3], lds64p(prm_nls + 3 * PRM_PAIR), lds64p(prm_c1h + 3 * PRM_PAIR), E, M2, NH);
+            }
+            // two-step class: this thread's 8 of the group's 16 predecessors, the partner (lane ^ 1) holds the rest
+            const float m2 = fmaxf(fmaxf(fmaxf(c2[0], c2[1]), fmaxf(c2[2], c2[3])), fmaxf(fmaxf(c2[4], c2[5]), fmaxf(c2[6], c2[7])));
+            const float m2o = __shfl_xor_sync(0xffffffffu, m2, 1);
+            // one-step class for h = 2t and 2t+1
+            const float v1a = __fadd_rn(w1a, fmaxf(fmaxf(o[0].x, o[1].x), fmaxf(o[2].x, o[3].x)));
+            const float v1b = __fadd_rn(w1b, fmaxf(fmaxf(o[0].y, o[1].y), fmaxf(o[2].y, o[3].y)));
+            f2 vs[SPT / 2];
 #pragma unroll
-            for (int k = 0; k < SPT; ++k)
-                a_own[k] = __fadd_rn(fmaxf(__fadd_rn(ws[k], a_own[k]), v12[k >> 2]), e_cur[k]);
-
-            float* An = sm.alpha[cur ^ 1];
-            *reinterpret_cast< float4* >(An + phys(j0)) = make_float4(a_own[0], a_own[1], a_own[2], a_own[3]);
-            *reinterpret_cast< float4* >(An + phys(j0 + 4)) = make_float4(a_own[4], a_own[5], a_own[6], a_own[7]);
-            if (keep) st_cs_v8(gcol, a_own);
+            for (int k = 0; k < SPT / 2; ++k) vs[k] = add2(ws[k], a_own[k]);   // self candidates
+            const float v2 = __fadd_rn(w2, fmaxf(m2, m2o));
+            const float va = fmaxf(v1a, v2), vb = fmaxf(v1b, v2);
+            a_own[0] = add2(pk(fmaxf(lo_of(vs[0]), va), fmaxf(hi_of(vs[0]), va)), e01[0]);
+            a_own[1] = add2(pk(fmaxf(lo_of(vs[1]), va), fmaxf(hi_of(vs[1]), va)), e01[1]);
+            a_own[2] = add2(pk(fmaxf(lo_of(vs[2]), vb), fmaxf(hi_of(vs[2]), vb)), e23[0]);
+            a_own[3] = add2(pk(fmaxf(lo_of(vs[3]), vb), fmaxf(hi_of(vs[3]), vb)), e23[1]);
+            float an[SPT];
+#pragma unroll
+            for (int k = 0; k < SPT / 2; ++k) { an[2 * k] = lo_of(a_own[k]); an[2 * k + 1] = hi_of(a_own[k]); }
+            sts128(wr_lo + WR, an[0], an[1], an[2], an[3]);
+            sts128(wr_hi + WR, an[4], an[5], an[6], an[7]);
+            if (keep) st_cs_v8(gcol, an);
             gcol += NC_N_STATES;
-            cur ^= 1;
-            // column i is published: arrive now, wait after the next event's emission
+            // ---- column i is published; part 2 runs in the barrier's shadow: pairs 0,1 of event i+1
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.col_bar);
-#pragma unroll
-            for (int k = 0; k < SPT; ++k) e_cur[k] = emission_h(P[k], E.x, E.y, y2, E.z, E.w, hl2pi);
-            mbar_wait(&sm.col_bar, col_phase & 1u);
-            ++col_phase;
+            mbar_arrive_if(bar, lane0);
+            {
+                const EvPairs E = ev_pairs(lds128(ev_b + (((i + 1) & (2 * CH - 1)) << 4)));
+                e01[0] = emission2(P[0], lds64p(prm_nls), lds64p(prm_c1h), E, M2, NH);
+                e01[1] = emission2(P[1], lds64p(prm_nls + PRM_PAIR), lds64p(prm_c1h + PRM_PAIR), E, M2, NH);
+            }
+            mbar_wait_u32(bar, decltype(cur_tag)::value);
+        };
+        {
+            unsigned i = 1;
+            for (; i + 1 < n; i += 2)
+            {
+                column(std::integral_constant< int, 0 >{}, i);
+                column(std::integral_constant< int, 1 >{}, i + 1);
+            }
+            if (i < n)
+            {
+                column(std::integral_constant< int, 0 >{}, i);
+                // an empty phase keeps the number of barrier phases per job even (parity == buffer index)
+                __syncwarp();
+                mbar_arrive_if(bar, lane0);
+                mbar_wait_u32(bar, 1);
+            }
         }
+        float a_fin[SPT];
+#pragma unroll
+        for (int k = 0; k < SPT / 2; ++k) { a_fin[2 * k] = lo_of(a_own[k]); a_fin[2 * k + 1] = hi_of(a_own[k]); }
 
         // ---------------- fill_state_seq: argmax over the last column, strict '>' ascending j (Viterbi.hpp:123-133)
         {
-            float bv = a_own[0];
+            float bv = a_fin[0];
             int bj = j0;
 #pragma unroll
             for (int k = 1; k < SPT; ++k)
-                if (a_own[k] > bv) { bv = a_own[k]; bj = j0 + k; }
+                if (a_fin[k] > bv) { bv = a_fin[k]; bj = j0 + k; }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1)
             {
