@@ -60,6 +60,10 @@ int nc_ctx_last_launches(nc_ctx* ctx);
  * Both produce the reference's bits; the switch exists for A/B measurements and tests. */
 typedef enum { NC_VIT_AUTO = 0, NC_VIT_BACKPOINTER = 2 } nc_vit_mode;
 int nc_ctx_set_viterbi_mode(nc_ctx* ctx, int mode);
+/* Device-side counters of the alpha-column kernel, summed over CTAs / traceback service warps since the last
+ * reset, in SM clock cycles: [0] forward passes, [1] forward CTAs waiting for a free slab, [2] traceback busy,
+ * [3] traceback waiting for work, then counts: [4] traceback passes, [5] traceback lane steps, [6] jobs traced. */
+int nc_ctx_viterbi_stats(nc_ctx* ctx, uint64_t* out8, int reset);
 /* number of SMs / name of the device, for reports */
 int nc_ctx_device_info(nc_ctx* ctx, int* n_sms, size_t* total_mem, char* name, int name_cap);
 

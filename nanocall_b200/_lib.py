@@ -55,6 +55,7 @@ SYMBOLS = {
     "nc_ctx_sync": (C.c_int, [_vp]),
     "nc_ctx_last_kernel_ms": (C.c_float, [_vp]),
     "nc_ctx_last_launches": (C.c_int, [_vp]),
+    "nc_ctx_viterbi_stats": (C.c_int, [_vp, _vp, C.c_int]),
     "nc_ctx_set_viterbi_mode": (C.c_int, [_vp, C.c_int]),
     "nc_ctx_device_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.c_char_p, C.c_int]),
     "nc_model_register": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),

@@ -84,6 +84,13 @@ class Context:
     def last_launches(self):
         return int(self.lib.nc_ctx_last_launches(self.h))
 
+    def viterbi_stats(self, reset=True):
+        """Counters of the alpha-column kernel (see nc_ctx_viterbi_stats)."""
+        out = np.zeros(8, np.uint64)
+        self._check(self.lib.nc_ctx_viterbi_stats(self.h, out.ctypes.data, int(reset)))
+        keys = ("fwd_cycles", "fwd_wait_slab_cycles", "tb_busy_cycles", "tb_wait_cycles", "tb_passes", "tb_lane_steps", "tb_jobs")
+        return {k: int(v) for k, v in zip(keys, out)}
+
     def set_viterbi_mode(self, mode):
         """L.NC_VIT_AUTO (alpha-column kernel where it fits) or L.NC_VIT_BACKPOINTER."""
         self._check(self.lib.nc_ctx_set_viterbi_mode(self.h, int(mode)))

@@ -44,7 +44,7 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
     {
         size_t free_b = 0, total_b = 0;
         if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return fail("cudaMemGetInfo", e);
-        bp_pool_bytes = std::min< size_t >(free_b / 2, (size_t)64 << 30);
+        bp_pool_bytes = std::min< size_t >(free_b / 5 * 3, (size_t)100 << 30);
     }
     bp_pool_bytes &= ~(size_t)4095;
     if ((e = cudaMalloc(&ctx->d_bp, bp_pool_bytes)) != cudaSuccess) return fail("cudaMalloc(backpointer pool)", e);
@@ -55,6 +55,8 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
     if ((e = cudaFuncSetAttribute(nc::viterbi_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)nc::viterbi_alpha_smem_bytes())) != cudaSuccess)
         return fail("cudaFuncSetAttribute(viterbi_alpha_kernel)", e);
+    if ((e = cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(stats)", e);
+    if ((e = cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset(stats)", e);
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
     unsigned hc = std::thread::hardware_concurrency();
     ctx->host_threads = hc ? std::min(hc, 32u) : 4u;
@@ -68,11 +70,12 @@ void nc_ctx_destroy(nc_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : { &ctx->jobs, &ctx->order, &ctx->counter, &ctx->path, &ctx->mean, &ctx->stdv, &ctx->start,
-                       &ctx->lstd, &ctx->states, &ctx->moves, &ctx->fb_scratch, &ctx->fb_seqs, &ctx->fb_groups, &ctx->fb_jobs,
+                       &ctx->lstd, &ctx->states, &ctx->moves, &ctx->tb, &ctx->fb_scratch, &ctx->fb_seqs, &ctx->fb_groups, &ctx->fb_jobs,
                        &ctx->fb_lz, &ctx->fb_pm, &ctx->fb_st, &ctx->fb_counter, &ctx->fb_mean, &ctx->fb_stdv, &ctx->fb_start, &ctx->fb_lstd })
         dev_free(*b);
     if (ctx->d_models) cudaFree(ctx->d_models);
     if (ctx->d_bp) cudaFree(ctx->d_bp);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_logsum_tbl) cudaFree(ctx->d_logsum_tbl);
     if (ctx->d_train_kmers) cudaFree(ctx->d_train_kmers);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -93,6 +96,16 @@ int nc_ctx_set_viterbi_mode(nc_ctx* ctx, int mode)
     if (!ctx) return NC_ERR_ARG;
     if (mode != NC_VIT_AUTO && mode != NC_VIT_BACKPOINTER) NC_FAIL(ctx, NC_ERR_ARG, "nc_ctx_set_viterbi_mode: bad mode %d", mode);
     ctx->vit_mode = mode;
+    return NC_OK;
+}
+
+int nc_ctx_viterbi_stats(nc_ctx* ctx, uint64_t* out8, int reset)
+{
+    if (!ctx || !out8) return NC_ERR_ARG;
+    NC_CUDA(ctx, cudaSetDevice(ctx->device));
+    NC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NC_CUDA(ctx, cudaMemcpy(out8, ctx->d_stats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) NC_CUDA(ctx, cudaMemset(ctx->d_stats, 0, 8 * sizeof(uint64_t)));
     return NC_OK;
 }
 
@@ -199,17 +212,21 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         }
     }
     // ---- which kernel decodes which job.  The alpha-column kernel is the fast path; it needs 16 KiB of scratch per
-    // event of every job in flight (one slab per CTA), the backpointer kernel 4 KiB.  With the pool cut into one slab
-    // per CTA, jobs that fit a slab as alpha columns take the fast path, longer ones the backpointer kernel.  A call
-    // that wants no states (candidate ranking by path probability) needs no scratch at all.
+    // event of every job in flight and two slabs per forward CTA (the traceback of one job overlaps the forward pass
+    // of the next); the backpointer kernel needs 4 KiB per event and one slab per CTA.  Jobs whose alpha columns fit
+    // a slab take the fast path, longer ones the backpointer kernel.  A call that wants no states (candidate
+    // ranking by path probability) needs no scratch at all.
     const bool want_path = states != nullptr || moves != nullptr;
     const size_t n_sms = (size_t)ctx->prop.multiProcessorCount;
-    const size_t ctas_wanted = std::min< size_t >(n_jobs, n_sms);
     const size_t a_col = (size_t)NC_N_STATES * sizeof(float), b_col = (size_t)NC_N_STATES;
+    // traceback service CTAs of the alpha kernel: one per ~36 forward CTAs (16 jobs in flight each)
+    auto tb_ctas_for = [&](size_t fwd) { return want_path ? std::min< size_t >(4, (fwd + 35) / 36) : (size_t)0; };
+    size_t fwd_wanted = std::min< size_t >(n_jobs, n_sms);
+    while (fwd_wanted > 1 && fwd_wanted + tb_ctas_for(fwd_wanted) > n_sms) --fwd_wanted;
     uint32_t alpha_max_len = 0xffffffffu;
     if (want_path)
-        alpha_max_len = (uint32_t)std::min< size_t >((ctx->bp_bytes / ctas_wanted) / a_col, 0xffffffffu);
-    if (ctx->vit_mode == 2) alpha_max_len = 0;   // forced backpointer form (tests, A/B measurements)
+        alpha_max_len = (uint32_t)std::min< size_t >((ctx->bp_bytes / (2 * fwd_wanted)) / a_col, 0xffffffffu);
+    if (ctx->vit_mode == NC_VIT_BACKPOINTER) alpha_max_len = 0;   // forced backpointer form (tests, A/B measurements)
     std::vector< unsigned > order(n_jobs);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return jobs[a].n_events > jobs[b].n_events; });
@@ -217,7 +234,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     uint32_t n_long = 0;
     while (n_long < n_jobs && jobs[order[n_long]].n_events > alpha_max_len) ++n_long;
     const uint32_t n_short = n_jobs - n_long;
-    unsigned grid_b = 0, grid_a = 0;
+    unsigned grid_b = 0, fwd_a = 0, tb_a = 0;
     size_t slab_b = 0, slab_a = 0;
     if (n_long)
     {
@@ -230,12 +247,14 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     }
     if (n_short)
     {
-        grid_a = (unsigned)std::min< size_t >(n_short, n_sms);
+        size_t fwd = std::min< size_t >(n_short, fwd_wanted);
         if (want_path)
         {
             slab_a = (size_t)jobs[order[n_long]].n_events * a_col;
-            grid_a = (unsigned)std::min< size_t >(grid_a, ctx->bp_bytes / slab_a);
+            fwd = std::min< size_t >(fwd, ctx->bp_bytes / (2 * slab_a));
         }
+        fwd_a = (unsigned)fwd;
+        tb_a = (unsigned)tb_ctas_for(fwd);
     }
 
     int rc;
@@ -259,6 +278,11 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     a.path_logprob = (float*)ctx->path.p;
     a.log_2pi = (float)std::log(2.0 * M_PI);
     a.log_n_states = std::log((float)NC_N_STATES);
+    a.n_fwd = 0;
+    a.n_tb = 0;
+    a.tickets = nullptr;
+    a.tb_tail = a.tb_head = a.slab_free = nullptr;
+    a.stats = ctx->d_stats;
 
     const uint64_t base = ev_off[0];
     if (mem == NC_MEM_HOST)
@@ -314,7 +338,21 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         b.n_jobs = n_short;
         b.next_job = a.next_job + 1;
         b.slab_bytes = slab_a;
-        nc::viterbi_alpha_kernel<<< grid_a, nc::VIT_THREADS, nc::viterbi_alpha_smem_bytes(), s >>>(b);
+        b.n_fwd = fwd_a;
+        b.n_tb = tb_a;
+        if (want_path)
+        {
+            // tickets | tail, head | per-slab release counters, zeroed
+            const size_t tk_bytes = (size_t)n_short * sizeof(nc::TbTicket);
+            const size_t ctl_bytes = (2 + 2 * (size_t)fwd_a) * sizeof(unsigned);
+            if ((rc = dev_reserve(ctx, ctx->tb, tk_bytes + ctl_bytes)) != NC_OK) return rc;
+            NC_CUDA(ctx, cudaMemsetAsync(ctx->tb.p, 0, tk_bytes + ctl_bytes, s));
+            b.tickets = (nc::TbTicket*)ctx->tb.p;
+            b.tb_tail = (unsigned*)((char*)ctx->tb.p + tk_bytes);
+            b.tb_head = b.tb_tail + 1;
+            b.slab_free = b.tb_tail + 2;
+        }
+        nc::viterbi_alpha_kernel<<< fwd_a + tb_a, nc::VIT_THREADS, nc::viterbi_alpha_smem_bytes(), s >>>(b);
         NC_CUDA(ctx, cudaGetLastError());
         ++ctx->last_launches;
     }

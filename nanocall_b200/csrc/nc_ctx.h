@@ -30,7 +30,7 @@ struct nc_ctx
     float* d_logsum_tbl = nullptr;
     std::string err;
     // grow-only scratch
-    DevBuf jobs, order, counter, path, mean, stdv, start, lstd, states, moves;
+    DevBuf jobs, order, counter, path, mean, stdv, start, lstd, states, moves, tb;
     DevBuf fb_scratch, fb_seqs, fb_groups, fb_jobs, fb_lz, fb_pm, fb_st, fb_counter, fb_mean, fb_stdv, fb_start, fb_lstd;
     unsigned* d_train_kmers = nullptr;
     unsigned n_train_kmers = 0;
@@ -39,6 +39,7 @@ struct nc_ctx
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_kernel_ms = 0.f;
     int last_launches = 0;        // kernels launched by the most recent nc_viterbi_packed
+    unsigned long long* d_stats = nullptr;   // 8 counters of the alpha kernel (nc_ctx_viterbi_stats)
     int vit_mode = 0;             // 0 = auto, 2 = backpointer kernel only (nc_ctx_set_viterbi_mode)
 };
 

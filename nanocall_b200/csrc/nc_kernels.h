@@ -9,6 +9,15 @@ namespace nc {
 
 enum { VIT_THREADS = 512 };
 
+// alpha-column kernel: a finished forward pass, queued for a traceback service warp
+struct TbTicket
+{
+    unsigned job;          // index into jobs
+    unsigned slab;         // slab holding the job's alpha columns
+    unsigned final_state;  // arg max of the last column
+    unsigned ready;        // written last (release); polled with acquire
+};
+
 struct VitArgs
 {
     const DevJob* jobs;
@@ -28,6 +37,16 @@ struct VitArgs
     unsigned char* moves;       // packed like the events, may be null
     float log_2pi;              // (float)log(2*pi)  (Pore_Model.hpp:28)
     float log_n_states;         // logf(4096.f)      (Viterbi.hpp:51)
+    // alpha-column kernel only: CTAs [0, n_tb) are traceback service warps fed through `tickets`, the other n_fwd
+    // CTAs run forward passes (two slabs each: 2*f, 2*f+1 for forward CTA f)
+    unsigned n_fwd, n_tb;
+    TbTicket* tickets;          // n_jobs entries, zeroed before the launch
+    unsigned* tb_tail;          // tickets published
+    unsigned* tb_head;          // tickets claimed
+    unsigned* slab_free;        // per slab: number of times a traceback released it
+    unsigned long long* stats;  // optional (may be null): [0] forward cycles, [1] forward cycles waiting for a slab,
+                                // [2] traceback busy cycles, [3] traceback cycles waiting for a ticket, [4] passes,
+                                // [5] lane steps, [6] jobs traced   (sums over CTAs / service warps)
 };
 
 __global__ void viterbi_kernel(const VitArgs a);        // backpointer form (long reads: 4 KiB/event of scratch)

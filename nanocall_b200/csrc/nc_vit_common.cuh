@@ -13,7 +13,7 @@ constexpr int THREADS = VIT_THREADS;   // 512
 constexpr int SPT = 8;                 // states per thread
 constexpr int CH = 128;                // events staged per chunk
 constexpr int ALPHA_PAD = 16;          // bank swizzle: upper half of the column shifted by 16 floats
-constexpr int TB_SPEC_DEPTH = 96;      // speculative look-back of the blocked traceback
+constexpr int TB_SPEC_DEPTH = 64;      // speculative look-back of the blocked traceback
 constexpr int TB_MIN_BLOCK = 64;
 
 // physical slot of alpha[j]: (1) the upper half of the column is shifted by 16 floats so the two threads of a

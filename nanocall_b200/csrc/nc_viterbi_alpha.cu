@@ -134,11 +134,8 @@ struct __align__(16) SmemA
     float alpha[2][NC_N_STATES + ALPHA_PAD];
     float4 ev[2 * CH];             // two chunks of staged events (slot = event index & 255)
     f2 prm[2][SPT / 2][THREADS];   // nls / c1h of every state pair, slot [.][pair][thread]: conflict-free LDS.64
-    float lut[64];                 // transition log-weights of the current job (traceback)
     float red_v[THREADS / 32];
     int red_j[THREADS / 32];
-    unsigned short tb_end[THREADS];
-    unsigned short tb_start[THREADS];
     unsigned job;
     int final_state;
     unsigned long long col_bar;    // mbarrier: one phase per event column
@@ -151,13 +148,20 @@ struct __align__(16) SmemA
 // is what the reference's strict '>' over the ascending from_v yields (Viterbi.hpp:78-89).
 __device__ __forceinline__ unsigned tb_step(const float* __restrict__ Ap, unsigned s, const float* lut)
 {
+    // column layout in the slab is group-major, G[g*16 + bb] = alpha[(bb<<8)|g]: the 16 two-step predecessors of s
+    // are one 64-byte line, its 4 one-step predecessors share another, the self predecessor sits in a third
     const unsigned g = s >> 4, h = s >> 2;
     float v2[16], v1[4];
+    const float4* q = reinterpret_cast< const float4* >(Ap + (g << 4));
 #pragma unroll
-    for (int bb = 0; bb < 16; ++bb) v2[bb] = __ldcg(Ap + (bb << 8) + g);
+    for (int k = 0; k < 4; ++k)
+    {
+        const float4 x = __ldcg(q + k);
+        v2[4 * k] = x.x; v2[4 * k + 1] = x.y; v2[4 * k + 2] = x.z; v2[4 * k + 3] = x.w;
+    }
 #pragma unroll
-    for (int b = 0; b < 4; ++b) v1[b] = __ldcg(Ap + (b << 10) + h);
-    const float v0 = __ldcg(Ap + s);
+    for (int b = 0; b < 4; ++b) v1[b] = __ldcg(Ap + ((h & 255u) << 4) + 4 * b + (h >> 8));   // alpha[(b<<10)|h]
+    const float v0 = __ldcg(Ap + ((s & 255u) << 4) + (s >> 8));                               // alpha[s]
     const float w2 = lut[trans_mask(g, s) & 0x3cu];
     const float w1 = lut[trans_mask(h, s) & 0x3eu];
     const float w0 = lut[trans_mask(s, s)];
@@ -183,9 +187,18 @@ __device__ __forceinline__ unsigned tb_step(const float* __restrict__ Ap, unsign
     return bp;
 }
 
-} // namespace
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
-__global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const VitArgs a)
+__device__ __forceinline__ void forward_cta(const VitArgs& a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemA& sm = *reinterpret_cast< SmemA* >(smem_raw);
@@ -195,8 +208,8 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
     const int warp = t >> 5;
     const unsigned j0 = SPT * t;
     const unsigned g = t >> 1;
-    float* const acol = reinterpret_cast< float* >(a.bp_pool + (size_t)blockIdx.x * a.slab_bytes);
     const bool keep = a.states != nullptr;   // path probability only: nothing to trace back, nothing stored
+    unsigned jobs_done = 0;
     const float log_2pi = a.log_2pi;
     const float hl2pi = __fmul_rn(0.5f, a.log_2pi);
     const unsigned bar = smem_u32(&sm.col_bar);
@@ -214,6 +227,22 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
         const DevJob& J = a.jobs[job_idx];
         const unsigned n = J.n_events;
         const unsigned long long off = J.ev_off;
+        // this job's slab: the CTA owns two and alternates; the previous user of the slab (job k-2 of this CTA) must
+        // have been traced back, i.e. the slab released (k >> 1) times so far
+        const unsigned slab_id = 2u * (blockIdx.x - a.n_tb) + (jobs_done & 1u);
+        float* const acol = reinterpret_cast< float* >(a.bp_pool + (size_t)slab_id * a.slab_bytes);
+        if (keep && jobs_done >= 2)
+        {
+            if (t == 0)
+            {
+                const long long c0 = clock64();
+                unsigned ns = 64;
+                while (ld_acquire_u32(a.slab_free + slab_id) < (jobs_done >> 1)) { __nanosleep(ns); if (ns < 4096) ns *= 2; }
+                if (a.stats) atomicAdd(a.stats + 1, (unsigned long long)(clock64() - c0));
+            }
+            __syncthreads();
+        }
+        const long long fwd_c0 = clock64();
 
         // ---------------- prologue: scaled model constants (as state pairs) and transition weights
         PairRegs P[SPT / 2];
@@ -245,7 +274,6 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
                 sm.prm[1][k / 2][t] = pk(x.c1h, y.c1h);
                 ws[k / 2] = pk(J.lut[trans_mask(j0 + k, j0 + k)], J.lut[trans_mask(j0 + k + 1, j0 + k + 1)]);
             }
-            if (t < 64) sm.lut[t] = J.lut[t];
         }
         // two-step weight of group g: mask bits 2..5 (bit 2 always set); one-step weight of h: bits 1..5
         const float w2 = J.lut[trans_mask(g, j0) & 0x3cu];
@@ -271,7 +299,6 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
             float* A = sm.alpha[0];
             *reinterpret_cast< float4* >(A + phys(j0)) = make_float4(a0[0], a0[1], a0[2], a0[3]);
             *reinterpret_cast< float4* >(A + phys(j0 + 4)) = make_float4(a0[4], a0[5], a0[6], a0[7]);
-            if (keep) st_cs_v8(acol + j0, a0);
         }
         // emission of event 1 for state pairs 0,1: carried into the loop (the loop computes it one event ahead)
         f2 e01[2];
@@ -291,7 +318,7 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
         const unsigned wr_lo = alpha0 + 4u * (unsigned)phys(j0), wr_hi = alpha0 + 4u * (unsigned)phys(j0 + 4);
         const unsigned ev_b = smem_u32(&sm.ev[0]);
         EvRegs pre = { 0.f, 1.f, 0.f, 0.f };
-        float* gcol = acol + NC_N_STATES + j0;                  // this thread's 8 slots of column i
+        float* gcol = acol + j0;                                // this thread's 8 slots of column i-1 (group-major)
         const unsigned lane0 = (lane == 0) ? 1u : 0u;
 
         auto column = [&](auto cur_tag, const unsigned i) {
@@ -307,6 +334,9 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
             float c2[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) c2[k] = lds32(two_b + RD + (k << 10));
+            // these 8 values are slots 8t..8t+7 of column i-1 in the slab's group-major layout: stream them out now
+            if (keep) st_cs_v8(gcol, c2);
+            gcol += NC_N_STATES;
             float2 o[4];
 #pragma unroll
             for (int b = 0; b < 4; ++b) o[b] = lds64(one_b + RD + (b << 12) + ((b >> 1) << 6));
@@ -337,8 +367,6 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
             for (int k = 0; k < SPT / 2; ++k) { an[2 * k] = lo_of(a_own[k]); an[2 * k + 1] = hi_of(a_own[k]); }
             sts128(wr_lo + WR, an[0], an[1], an[2], an[3]);
             sts128(wr_hi + WR, an[4], an[5], an[6], an[7]);
-            if (keep) st_cs_v8(gcol, an);
-            gcol += NC_N_STATES;
             // ---- column i is published; part 2 runs in the barrier's shadow: pairs 0,1 of event i+1
             __syncwarp();
             mbar_arrive_if(bar, lane0);
@@ -364,6 +392,15 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
                 mbar_arrive_if(bar, lane0);
                 mbar_wait_u32(bar, 1);
             }
+        }
+        if (keep)
+        {
+            // the last column (buffer (n-1) & 1), in the same group-major order
+            float c2[8];
+            const unsigned RDL = ((n - 1) & 1u) * COL_BYTES;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c2[k] = lds32(two_b + RDL + (k << 10));
+            st_cs_v8(gcol, c2);
         }
         float a_fin[SPT];
 #pragma unroll
@@ -397,72 +434,138 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
             __syncthreads();
         }
 
-        // ---------------- traceback (Viterbi.hpp:134-142): blocked and speculative as in viterbi_kernel, but every
-        // step evaluates the arg max from the stored column i-1 (tb_step) instead of decoding a stored byte.
+        // ---------------- hand the traceback to a service warp (other CTAs of this grid) and go on with the next job.
+        // The alpha columns of this job stay in the slab until the service warp releases it; the CTA alternates
+        // between its two slabs, so the forward pass of job k+1 overlaps the traceback of job k.
         if (keep)
         {
-            const unsigned T = n - 1;  // transitions: column c in 1..T is entered from column c-1
-            unsigned short* out_s = a.states + off;
-            if (T == 0)
-            {
-                if (t == 0) out_s[0] = (unsigned short)sm.final_state;
-            }
-            else
-            {
-                unsigned B = (T + THREADS - 1) / THREADS;
-                if (B < (unsigned)TB_MIN_BLOCK) B = TB_MIN_BLOCK;
-                const unsigned nb = (T + B - 1) / B;
-                const unsigned lo = (unsigned)t * B;
-                const unsigned hi = (lo + B < T) ? lo + B : T;
-                const bool active = (unsigned)t < nb;
-                if (active)
-                {
-                    unsigned s;
-                    if (hi == T) s = sm.final_state;
-                    else
-                    {
-                        unsigned c = hi + TB_SPEC_DEPTH;
-                        if (c >= T) { c = T; s = sm.final_state; }
-                        else s = 0;
-                        for (; c > hi; --c) s = tb_step(acol + (size_t)(c - 1) * NC_N_STATES, s, sm.lut);
-                    }
-                    sm.tb_end[t] = (unsigned short)s;
-                }
-                __syncthreads();
-                bool dirty = active;  // first pass: everyone walks
-                for (;;)
-                {
-                    if (dirty)
-                    {
-                        unsigned s = sm.tb_end[t];
-                        out_s[hi] = (unsigned short)s;
-                        for (unsigned c = hi; c > lo; --c)
-                        {
-                            s = tb_step(acol + (size_t)(c - 1) * NC_N_STATES, s, sm.lut);
-                            if (c - 1 > lo || t == 0) out_s[c - 1] = (unsigned short)s;
-                        }
-                        sm.tb_start[t] = (unsigned short)s;
-                    }
-                    __syncthreads();
-                    dirty = false;
-                    if (active && (unsigned)t + 1 < nb && sm.tb_end[t] != sm.tb_start[t + 1]) dirty = true;
-                    const int any = __syncthreads_or(dirty ? 1 : 0);
-                    if (!any) break;
-                    if (dirty) sm.tb_end[t] = sm.tb_start[t + 1];
-                    __syncthreads();
-                }
-            }
-            // ---------------- fill_move_seq (Viterbi.hpp:144-150)
+            __threadfence();        // every thread: its alpha stores are visible device-wide before the ticket is
             __syncthreads();
-            if (a.moves != nullptr)
+            if (t == 0)
             {
-                unsigned char* out_m = a.moves + off;
-                for (unsigned i = t; i < n; i += THREADS)
-                    out_m[i] = (i == 0) ? 0 : (unsigned char)min_skip(out_s[i - 1], out_s[i]);
+                const unsigned slot = atomicAdd(a.tb_tail, 1u);
+                TbTicket& tk = a.tickets[slot];
+                tk.job = job_idx;
+                tk.slab = slab_id;
+                tk.final_state = (unsigned)sm.final_state;
+                __threadfence();
+                st_release_u32(&tk.ready, 1u);
             }
         }
-        __syncthreads();
+        ++jobs_done;
+        if (t == 0 && a.stats) atomicAdd(a.stats + 0, (unsigned long long)(clock64() - fwd_c0));
     }
+}
+
+// ---------------- traceback service (Viterbi.hpp:134-150).  One warp per job: the chain s[c-1] = pred(s[c]) is cut
+// into <= 32 blocks, one per lane.  A lane starts from a GUESS of its block's end state, obtained by walking back
+// TB_SPEC_DEPTH columns from an arbitrary state (survivor paths coalesce quickly); all lanes walk in parallel;
+// guesses are verified against the state the successor block actually reached and wrong blocks are re-walked until
+// nothing changes -- exactly the sequential traceback, in ~(n/32 + depth) dependent steps.  Every step evaluates
+// the arg max from the stored alpha column (tb_step).
+__device__ void traceback_service(const VitArgs& a)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;)
+    {
+        unsigned h = 0;
+        if (lane == 0) h = atomicAdd(a.tb_head, 1u);
+        h = __shfl_sync(0xffffffffu, h, 0);
+        if (h >= a.n_jobs) return;
+        TbTicket& tk = a.tickets[h];
+        const long long w0 = clock64();
+        if (lane == 0)
+        {
+            unsigned ns = 64;
+            while (ld_acquire_u32(&tk.ready) == 0u) { __nanosleep(ns); if (ns < 2048) ns *= 2; }
+        }
+        __syncwarp();
+        const long long w1 = clock64();
+        unsigned passes = 0, steps = 0;
+        const unsigned job_idx = __ldcg(&tk.job), slab_id = __ldcg(&tk.slab), final_state = __ldcg(&tk.final_state);
+        const DevJob& J = a.jobs[job_idx];
+        const unsigned n = J.n_events;
+        const float* lut = J.lut;
+        const float* acol = reinterpret_cast< const float* >(a.bp_pool + (size_t)slab_id * a.slab_bytes);
+        unsigned short* out_s = a.states + J.ev_off;
+        const unsigned T = n - 1;  // transitions: column c in 1..T is entered from column c-1
+        if (T == 0)
+        {
+            if (lane == 0) out_s[0] = (unsigned short)final_state;
+        }
+        else
+        {
+            unsigned B = (T + 31) / 32;
+            if (B < (unsigned)TB_MIN_BLOCK) B = TB_MIN_BLOCK;
+            const unsigned nb = (T + B - 1) / B;
+            const unsigned lo = (unsigned)lane * B;
+            const unsigned hi = (lo + B < T) ? lo + B : T;
+            const bool active = (unsigned)lane < nb;
+            unsigned end_s = final_state, start_s = 0;
+            if (active && hi != T)
+            {
+                unsigned c = hi + TB_SPEC_DEPTH;
+                unsigned s = 0;
+                if (c >= T) { c = T; s = final_state; }
+                steps += c - hi;
+                for (; c > hi; --c) s = tb_step(acol + (size_t)(c - 1) * NC_N_STATES, s, lut);
+                end_s = s;
+            }
+            bool dirty = active;  // first pass: every lane walks its block
+            for (;;)
+            {
+                ++passes;
+                if (dirty)
+                {
+                    unsigned s = end_s;
+                    steps += hi - lo;
+                    out_s[hi] = (unsigned short)s;
+                    for (unsigned c = hi; c > lo; --c)
+                    {
+                        s = tb_step(acol + (size_t)(c - 1) * NC_N_STATES, s, lut);
+                        if (c - 1 > lo || lane == 0) out_s[c - 1] = (unsigned short)s;
+                    }
+                    start_s = s;
+                }
+                __syncwarp();
+                const unsigned next_start = __shfl_down_sync(0xffffffffu, start_s, 1);
+                dirty = active && (unsigned)lane + 1 < nb && end_s != next_start;
+                if (!__any_sync(0xffffffffu, dirty)) break;
+                if (dirty) end_s = next_start;
+            }
+        }
+        __threadfence();   // states visible to the lanes that derive the moves; slab reads are complete
+        __syncwarp();
+        if (lane == 0) atomicAdd(a.slab_free + slab_id, 1u);
+        if (a.stats)
+        {
+            for (int d = 16; d > 0; d >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, d);
+            if (lane == 0)
+            {
+                atomicAdd(a.stats + 2, (unsigned long long)(clock64() - w1));
+                atomicAdd(a.stats + 3, (unsigned long long)(w1 - w0));
+                atomicAdd(a.stats + 4, (unsigned long long)passes);
+                atomicAdd(a.stats + 5, (unsigned long long)steps);
+                atomicAdd(a.stats + 6, 1ull);
+            }
+        }
+        // ---------------- fill_move_seq (Viterbi.hpp:144-150)
+        if (a.moves != nullptr)
+        {
+            unsigned char* out_m = a.moves + J.ev_off;
+            for (unsigned i = lane; i < n; i += 32)
+                out_m[i] = (i == 0) ? 0 : (unsigned char)min_skip(__ldcg(out_s + i - 1), __ldcg(out_s + i));
+        }
+    }
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const VitArgs a)
+{
+    // service CTAs take the lowest block indices so they are resident before any forward CTA can wait on them
+    if (blockIdx.x < a.n_tb) traceback_service(a);
+    else forward_cta(a);
 }
 
 size_t viterbi_alpha_smem_bytes() { return sizeof(SmemA); }

@@ -16,3 +16,4 @@ for name, kw in modes:
         ctx.viterbi_device(batch["ev_off"], d["mean"].data_ptr(), d["stdv"].data_ptr(), d["start"].data_ptr(), None, mid, **kw)
         ms = ctx.last_kernel_ms()
     print(name, "kernel ms", ms, "Mev/s", R*N/ms/1e3, flush=True)
+    print(ctx.viterbi_stats(), flush=True)
