@@ -286,13 +286,14 @@ def main():
             "config": {"workload": f"{args.reads} reads x {args.events} events per GPU, R7.3 template, "
                                    "fixed identity scaling, default transitions, Viterbi + traceback (configs[1])",
                        "model": MODEL, "reads_per_gpu": args.reads, "events_per_read": args.events,
-                       "l2": "inputs (1.2 GB events per 1e8 events + 41 MB backpointers per read) larger than L2",
+                       "l2": "inputs larger than L2: 12 B/event of events (1.2 GB per 1e8 events) and 16 KiB/event of alpha columns (164 MB per 10k-event read) stream through HBM, nothing is reused across steps",
                        "device": info["name"], "n_sms": info["n_sms"]},
             "clocks": clocks,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind,
-                         "kernel": "viterbi_kernel", "algorithmic_bytes_per_event": HBM_BYTES_PER_EVENT},
+                         "kernel": "viterbi_kernel" if args.vit_mode == "backpointer" else "viterbi_alpha_kernel",
+                         "algorithmic_bytes_per_event": HBM_BYTES_PER_EVENT},
             "roofline_fp32": {"bound": "fp32_issue", "achieved": per_gpu_evs * FP32_OPS_PER_EVENT / 1e12,
                               "peak": fp32_peak, "unit": "Tinstr/s", "frac": per_gpu_evs * FP32_OPS_PER_EVENT / 1e12 / fp32_peak,
                               "algorithmic_ops_per_event": FP32_OPS_PER_EVENT,

@@ -1,0 +1,21 @@
+#!/bin/bash
+# One GPU session: parity tests, the bench line, the ncu launch list and one full capture of the dominant kernel.
+# usage (under gpurun): bash tools/gpu_round.sh <tag>
+set -u
+tag=${1:-run}
+out=gpurun_out/$tag
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > $out/gpu.txt 2>&1
+lscpu | head -20 > $out/cpu.txt 2>&1
+( time python -m pytest tests -m gpu -x -q ) > $out/pytest.log 2>&1
+tail -3 $out/pytest.log
+python bench.py > $out/bench.json 2> $out/bench.err
+cat $out/bench.json
+python bench.py --impl reference --steps 1 --warmup 0 > $out/bench_ref.json 2>> $out/bench.err
+cat $out/bench_ref.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
+    python bench.py --steps 2 --warmup 1 --reads 1500 --no-cpu-baseline --no-e2e > $out/launches_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:viterbi_alpha -c 1 -f -o $out/vit_alpha \
+    python bench.py --reads 296 --events 3000 --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $out/ncu_full.log 2>&1
+tail -2 $out/ncu_full.log
+ls -la $out
