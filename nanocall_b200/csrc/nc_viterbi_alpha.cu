@@ -54,8 +54,8 @@ __device__ __forceinline__ void st_cs_v8(float* p, const float (&v)[8])
 // emission keeps the reference's bits (tests/test_viterbi_gpu.py runs every case through this kernel).
 typedef unsigned long long f2;
 __device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ float lo_of(f2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi_of(f2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ float lo_of(f2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); (void)b; return a; }
+__device__ __forceinline__ float hi_of(f2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); (void)a; return b; }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
@@ -99,18 +99,12 @@ __device__ __forceinline__ EvPairs ev_pairs(const float4& s)
 }
 // shared-memory access by 32-bit shared address: one base register + immediate offset in SASS, no generic-address
 // arithmetic.  volatile: ordered against the barrier asm statements.
-__device__ __forceinline__ float lds32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ float2 lds64(unsigned a) { float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ f2 lds64p(unsigned a) { f2 v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
 __device__ __forceinline__ float4 lds128(unsigned a)
 {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
-}
-__device__ __forceinline__ void sts128(unsigned a, float x, float y, float z, float w)
-{
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_if(unsigned bar, unsigned pred)
 {
@@ -129,10 +123,47 @@ __device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity)
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// Event staging without registers held across columns: request = 4-byte cp.async of the raw fields into shared
+// memory, collect = wait for the own copies and read them back (same thread, so no barrier is needed).
+__device__ __forceinline__ void cp_async4(unsigned dst, const float* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ev_request(const VitArgs& a, unsigned raw_b, unsigned long long off, unsigned i, unsigned n)
+{
+    if (i < n)
+    {
+        cp_async4(raw_b, a.mean + off + i);
+        cp_async4(raw_b + CH * 4, a.stdv + off + i);
+        cp_async4(raw_b + 2 * CH * 4, a.start + off + i);
+        if (a.log_stdv) cp_async4(raw_b + 3 * CH * 4, a.log_stdv + off + i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ EvRegs ev_collect(const VitArgs& a, const float (&raw)[4][CH], int slot, unsigned i, unsigned n)
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    EvRegs r;
+    if (i < n)
+    {
+        r.mean = raw[0][slot]; r.stdv = raw[1][slot]; r.start = raw[2][slot];
+        r.lstd = a.log_stdv ? raw[3][slot] : nc_logf(r.stdv == 0.0f ? 0.01f : r.stdv);
+    }
+    else { r.mean = 0.f; r.stdv = 1.f; r.start = 0.f; r.lstd = 0.f; }
+    return r;
+}
+
+// Exchange buffers of one column: the class candidates, already weighted, of every predecessor group.
+//   x2[G], G = j >> 4  (256 two-step groups):  RN(w2(G) + max_bb alpha[(bb << 8) | G])
+//   x1[H], H = j >> 2  (1024 one-step groups): RN(w1(H) + max_b  alpha[(b << 10) | H])
+// stored so that the 4 + 4 values a thread needs for four of its states are one LDS.128 each (pos_x2 / pos_x1).
+constexpr unsigned X2_FLOATS = 16 * 16 + 8 * 4, X1_FLOATS = 64 * 16 + 32 * 4;   // rows of 16 floats + the row skew
 struct __align__(16) SmemA
 {
-    float alpha[2][NC_N_STATES + ALPHA_PAD];
+    float x2[2][X2_FLOATS];
+    float x1[2][X1_FLOATS];
     float4 ev[2 * CH];             // two chunks of staged events (slot = event index & 255)
+    float raw[4][CH];              // next chunk as read from HBM (mean, stdv, start, log_stdv), filled by cp.async
     f2 prm[2][SPT / 2][THREADS];   // nls / c1h of every state pair, slot [.][pair][thread]: conflict-free LDS.64
     float red_v[THREADS / 32];
     int red_j[THREADS / 32];
@@ -141,17 +172,62 @@ struct __align__(16) SmemA
     unsigned long long col_bar;    // mbarrier: one phase per event column
 };
 
-// One traceback step: the predecessor of state s, given the alpha column of the previous event.
+// Ownership ("source-group" mapping).  Thread t = 2 T + half owns the 8 states
+//     j(k) = (b << 10) | (b' << 8) | T,   b = k & 3,  b' = 2 half + (k >> 2),   k = 0..7
+// i.e. half of the 16 states whose low 8 bits are T.  Those 16 states are exactly the two-step predecessors of
+// group G = T, and for each b' the four states b = 0..3 are exactly the one-step predecessors of group
+// H = (b' << 8) | T.  So the maxima over predecessor classes are taken on the thread's OWN registers (the alpha
+// values it produced for the previous column) -- one shuffle with the partner thread (lane ^ 1) completes the
+// two-step group -- and only the weighted class candidates (5 KiB per column instead of the 16 KiB column plus
+// 32 KiB of predecessor reads) go through shared memory.
+__device__ __forceinline__ unsigned own_state(unsigned T, unsigned half, unsigned k)
+{
+    return ((k & 3u) << 10) | ((2u * half + (k >> 2)) << 8) | T;
+}
+// float index of group G = (b << 6) | (b' << 4) | x in x2: row x = 16 floats, column b' * 4 + b, rows skewed by
+// 4 floats per two rows.  A reader (x = T >> 4, b' fixed) gets b = 0..3 with one LDS.128, its second b' sits 16
+// bytes further; the skew keeps the readers of x1 conflict-free (4 consecutive rows x 2 halves hit 8 different
+// 16-byte bank groups) and the writers 2-way at worst.  Every address is `one register + immediate` in the loop.
+__device__ __forceinline__ unsigned pos_x2(unsigned G)
+{
+    const unsigned x = G & 15u, bq = (G >> 4) & 3u, b = G >> 6;
+    return x * 16u + (x >> 1) * 4u + bq * 4u + b;
+}
+// float index of group H = (b << 8) | (b' << 6) | x in x1: same form with 64 rows
+__device__ __forceinline__ unsigned pos_x1(unsigned H)
+{
+    const unsigned x = H & 63u, bq = (H >> 6) & 3u, b = H >> 8;
+    return x * 16u + (x >> 1) * 4u + bq * 4u + b;
+}
+// slot of alpha[s] inside a stored column: thread-major, (s & 255) * 16 + ((s >> 8) & 3) * 4 + (s >> 10)
+__device__ __forceinline__ unsigned slab_pos(unsigned s) { return ((s & 255u) << 4) | (((s >> 8) & 3u) << 2) | (s >> 10); }
+
+__device__ __forceinline__ float max3(float a, float b, float c)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ void sts32_if(unsigned a, float x, unsigned pred)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.f32 [%0], %1;\n}" ::"r"(a), "f"(x), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void sts64(unsigned a, float x, float y)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+
+// One traceback step: the predecessor of state s, given the stored alpha column of the previous event.
 // Candidates as in the forward pass (two-step class weight w2(g), one-step class weight w1(h), exact self weight);
 // a predecessor that belongs to two classes appears twice with the same index and a weight <= its exact one, which
 // changes neither the maximum nor the lowest index attaining it (see nc_viterbi.cu).  Ties -> lowest index, which
 // is what the reference's strict '>' over the ascending from_v yields (Viterbi.hpp:78-89).
 __device__ __forceinline__ unsigned tb_step(const float* __restrict__ Ap, unsigned s, const float* lut)
 {
-    // column layout in the slab is group-major, G[g*16 + bb] = alpha[(bb<<8)|g]: the 16 two-step predecessors of s
-    // are one 64-byte line, its 4 one-step predecessors share another, the self predecessor sits in a third
+    // column layout (slab_pos): the 16 two-step predecessors of s are one 64-byte line (slot b' * 4 + b for
+    // predecessor bb = 4 b + b'), its 4 one-step predecessors one aligned float4, the self predecessor a third line
     const unsigned g = s >> 4, h = s >> 2;
-    float v2[16], v1[4];
+    float v2[16];
     const float4* q = reinterpret_cast< const float4* >(Ap + (g << 4));
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -159,9 +235,9 @@ __device__ __forceinline__ unsigned tb_step(const float* __restrict__ Ap, unsign
         const float4 x = __ldcg(q + k);
         v2[4 * k] = x.x; v2[4 * k + 1] = x.y; v2[4 * k + 2] = x.z; v2[4 * k + 3] = x.w;
     }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) v1[b] = __ldcg(Ap + ((h & 255u) << 4) + 4 * b + (h >> 8));   // alpha[(b<<10)|h]
-    const float v0 = __ldcg(Ap + ((s & 255u) << 4) + (s >> 8));                               // alpha[s]
+    const float4 o = __ldcg(reinterpret_cast< const float4* >(Ap + (((h & 255u) << 4) | ((h >> 8) << 2))));   // alpha[(b<<10)|h]
+    const float v1[4] = { o.x, o.y, o.z, o.w };
+    const float v0 = __ldcg(Ap + slab_pos(s));                                                                  // alpha[s]
     const float w2 = lut[trans_mask(g, s) & 0x3cu];
     const float w1 = lut[trans_mask(h, s) & 0x3eu];
     const float w0 = lut[trans_mask(s, s)];
@@ -170,7 +246,7 @@ __device__ __forceinline__ unsigned tb_step(const float* __restrict__ Ap, unsign
 #pragma unroll
     for (int bb = 1; bb < 16; ++bb)
     {
-        const float c = __fadd_rn(w2, v2[bb]);
+        const float c = __fadd_rn(w2, v2[(bb & 3) * 4 + (bb >> 2)]);
         if (c > best) { best = c; bp = ((unsigned)bb << 8) | g; }
     }
 #pragma unroll
@@ -206,8 +282,7 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
     const int t = threadIdx.x;
     const int lane = t & 31;
     const int warp = t >> 5;
-    const unsigned j0 = SPT * t;
-    const unsigned g = t >> 1;
+    const unsigned T = (unsigned)t >> 1, half = (unsigned)t & 1u;
     const bool keep = a.states != nullptr;   // path probability only: nothing to trace back, nothing stored
     unsigned jobs_done = 0;
     const float log_2pi = a.log_2pi;
@@ -251,95 +326,106 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
         constexpr unsigned PRM_PAIR = THREADS * sizeof(f2);   // byte stride between the pairs of one thread
         {
             const float* M = a.models + (size_t)J.model * MODEL_FLOATS;
-            float lm[SPT], ls[SPT], sdm[SPT], sdl[SPT], lls[SPT], lsl[SPT];
-#pragma unroll
-            for (int v = 0; v < SPT / 4; ++v)
-            {
-                *reinterpret_cast< float4* >(lm + 4 * v) = __ldg(reinterpret_cast< const float4* >(M + 0 * NC_N_STATES + j0) + v);
-                *reinterpret_cast< float4* >(ls + 4 * v) = __ldg(reinterpret_cast< const float4* >(M + 1 * NC_N_STATES + j0) + v);
-                *reinterpret_cast< float4* >(sdm + 4 * v) = __ldg(reinterpret_cast< const float4* >(M + 2 * NC_N_STATES + j0) + v);
-                *reinterpret_cast< float4* >(sdl + 4 * v) = __ldg(reinterpret_cast< const float4* >(M + 3 * NC_N_STATES + j0) + v);
-                *reinterpret_cast< float4* >(lls + 4 * v) = __ldg(reinterpret_cast< const float4* >(M + 4 * NC_N_STATES + j0) + v);
-                *reinterpret_cast< float4* >(lsl + 4 * v) = __ldg(reinterpret_cast< const float4* >(M + 5 * NC_N_STATES + j0) + v);
-            }
 #pragma unroll
             for (int k = 0; k < SPT; k += 2)
             {
-                const StateParamsH x = halve(scale_state(lm[k], ls[k], sdm[k], sdl[k], lls[k], lsl[k], J, log_2pi));
-                const StateParamsH y = halve(scale_state(lm[k + 1], ls[k + 1], sdm[k + 1], sdl[k + 1], lls[k + 1], lsl[k + 1], J, log_2pi));
+                const unsigned ja = own_state(T, half, k), jb = own_state(T, half, k + 1);
+                const StateParamsH x = halve(scale_state(__ldg(M + 0 * NC_N_STATES + ja), __ldg(M + 1 * NC_N_STATES + ja),
+                                                         __ldg(M + 2 * NC_N_STATES + ja), __ldg(M + 3 * NC_N_STATES + ja),
+                                                         __ldg(M + 4 * NC_N_STATES + ja), __ldg(M + 5 * NC_N_STATES + ja), J, log_2pi));
+                const StateParamsH y = halve(scale_state(__ldg(M + 0 * NC_N_STATES + jb), __ldg(M + 1 * NC_N_STATES + jb),
+                                                         __ldg(M + 2 * NC_N_STATES + jb), __ldg(M + 3 * NC_N_STATES + jb),
+                                                         __ldg(M + 4 * NC_N_STATES + jb), __ldg(M + 5 * NC_N_STATES + jb), J, log_2pi));
                 PairRegs& p = P[k / 2];
                 p.nmu = pk(-x.mu, -y.mu); p.nsg2 = pk(-x.sg2, -y.sg2); p.rsgh = pk(x.rsgh, y.rsgh);
                 p.neta = pk(-x.eta, -y.eta); p.reta = pk(x.reta, y.reta); p.lam = pk(x.lam, y.lam);
                 sm.prm[0][k / 2][t] = pk(x.nls, y.nls);      // read back by this thread only
                 sm.prm[1][k / 2][t] = pk(x.c1h, y.c1h);
-                ws[k / 2] = pk(J.lut[trans_mask(j0 + k, j0 + k)], J.lut[trans_mask(j0 + k + 1, j0 + k + 1)]);
+                ws[k / 2] = pk(J.lut[trans_mask(ja, ja)], J.lut[trans_mask(jb, jb)]);
             }
         }
-        // two-step weight of group g: mask bits 2..5 (bit 2 always set); one-step weight of h: bits 1..5
-        const float w2 = J.lut[trans_mask(g, j0) & 0x3cu];
-        const float w1a = J.lut[trans_mask(2 * t, j0) & 0x3eu];
-        const float w1b = J.lut[trans_mask(2 * t + 1, j0 + 4) & 0x3eu];
+        // class weights of the groups this thread publishes: two-step group G = T (mask bits 2..5, bit 2 always
+        // set), one-step groups H = (b' << 8) | T for its two b' (mask bits 1..5)
+        const float w2 = J.lut[trans_mask(T, T << 4) & 0x3cu];
+        const unsigned Ha = ((2u * half) << 8) | T, Hb = ((2u * half + 1u) << 8) | T;
+        const float w1a = J.lut[trans_mask(Ha, Ha << 2) & 0x3eu];
+        const float w1b = J.lut[trans_mask(Hb, Hb << 2) & 0x3eu];
         const f2 M2 = pk(-2.0f, -2.0f), NH = pk(-hl2pi, -hl2pi);
 
+        // shared-memory addresses of the exchange slots (buffer 0; buffer 1 is + X2_BUF / X1_BUF bytes)
+        constexpr unsigned X2_BUF = X2_FLOATS * sizeof(float), X1_BUF = X1_FLOATS * sizeof(float);
+        const unsigned x2_0 = smem_u32(&sm.x2[0][0]), x1_0 = smem_u32(&sm.x1[0][0]);
+        const unsigned wr_x2 = x2_0 + 4u * pos_x2(T);                       // written by the half == 0 thread
+        const unsigned wr_x1 = x1_0 + 4u * pos_x1(Ha);                      // Ha, Hb are adjacent floats
+        // candidates of states k = 0..3 (b' = 2 half) and k = 4..7 (b' = 2 half + 1): one float4 each per class
+        // (the float4 of b' = 2 half + 1 lies 16 bytes after the one of b' = 2 half)
+        const unsigned rd_x2 = x2_0 + 4u * pos_x2(((2u * half) << 4) | (T >> 4));
+        const unsigned rd_x1 = x1_0 + 4u * pos_x1(((2u * half) << 6) | (T >> 2));
+        const unsigned ev_b = smem_u32(&sm.ev[0]);
+        const unsigned lane0 = (lane == 0) ? 1u : 0u, half0 = half ^ 1u;
+        float* gcol = acol + SPT * t;                                       // this thread's 8 slots of a stored column
+
+        // publish<B>: from column i-1 (a_own) the weighted class candidates of column i into buffer B; stream
+        // column i-1 to the slab; arrive on the column barrier
+        f2 a_own[SPT / 2];
+        auto publish = [&](auto buf_tag) {
+            constexpr unsigned B = decltype(buf_tag)::value;
+            const float m1a = max3(fmaxf(lo_of(a_own[0]), hi_of(a_own[0])), lo_of(a_own[1]), hi_of(a_own[1]));
+            const float m1b = max3(fmaxf(lo_of(a_own[2]), hi_of(a_own[2])), lo_of(a_own[3]), hi_of(a_own[3]));
+            const float m2h = fmaxf(m1a, m1b);
+            const float m2o = __shfl_xor_sync(0xffffffffu, m2h, 1);
+            if (keep)
+            {
+                const float c[8] = { lo_of(a_own[0]), hi_of(a_own[0]), lo_of(a_own[1]), hi_of(a_own[1]),
+                                     lo_of(a_own[2]), hi_of(a_own[2]), lo_of(a_own[3]), hi_of(a_own[3]) };
+                st_cs_v8(gcol, c);
+            }
+            gcol += NC_N_STATES;
+            sts64(wr_x1 + B * X1_BUF, __fadd_rn(w1a, m1a), __fadd_rn(w1b, m1b));
+            sts32_if(wr_x2 + B * X2_BUF, __fadd_rn(w2, fmaxf(m2h, m2o)), half0);
+            __syncwarp();
+            mbar_arrive_if(bar, lane0);
+        };
+
         // ---------------- first chunk of events, column 0 (Viterbi.hpp:57-67)
+        asm volatile("cp.async.wait_all;" ::: "memory");   // a request of the previous job that was never collected
         if (t < CH) sm.ev[t] = ev_slot(ev_pack(ev_load(a, off, t, n), J.drift));
         __syncthreads();
-        f2 a_own[SPT / 2];
         {
             const EvPairs E = ev_pairs(sm.ev[0]);
             const f2 nlog_n = pk(-a.log_n_states, -a.log_n_states);
-            float a0[SPT];
 #pragma unroll
             for (int k = 0; k < SPT / 2; ++k)
-            {
                 a_own[k] = add2(emission2(P[k], sm.prm[0][k][t], sm.prm[1][k][t], E, M2, NH), nlog_n);
-                a0[2 * k] = lo_of(a_own[k]);
-                a0[2 * k + 1] = hi_of(a_own[k]);
-            }
-            float* A = sm.alpha[0];
-            *reinterpret_cast< float4* >(A + phys(j0)) = make_float4(a0[0], a0[1], a0[2], a0[3]);
-            *reinterpret_cast< float4* >(A + phys(j0 + 4)) = make_float4(a0[4], a0[5], a0[6], a0[7]);
         }
-        // emission of event 1 for state pairs 0,1: carried into the loop (the loop computes it one event ahead)
+        // candidates of column 1 -> buffer 1 (phase 0 of this job); then, in the barrier's shadow, the emission of
+        // event 1 for state pairs 0,1 (the loop keeps computing them one step ahead)
+        publish(std::integral_constant< unsigned, 1 >{});
         f2 e01[2];
         {
             const EvPairs E = ev_pairs(sm.ev[1]);
             e01[0] = emission2(P[0], sm.prm[0][0][t], sm.prm[1][0][t], E, M2, NH);
             e01[1] = emission2(P[1], sm.prm[0][1][t], sm.prm[1][1][t], E, M2, NH);
         }
-        __syncthreads();
+        mbar_wait_u32(bar, 0);
 
         // ---------------- columns 1..n-1 (Viterbi.hpp:72-96), max only
-        constexpr unsigned COL_BYTES = (NC_N_STATES + ALPHA_PAD) * sizeof(float);
-        const unsigned alpha0 = smem_u32(&sm.alpha[0][0]);
-        const int half = t & 1;
-        const unsigned two_b = alpha0 + 4u * (unsigned)phys(((8 * half) << 8) + (int)g);  // this thread's 8 two-step predecessors
-        const unsigned one_b = alpha0 + 4u * (unsigned)phys(2 * t);                        // + (b<<10) + ((b>>1)<<4) floats, b = 0..3
-        const unsigned wr_lo = alpha0 + 4u * (unsigned)phys(j0), wr_hi = alpha0 + 4u * (unsigned)phys(j0 + 4);
-        const unsigned ev_b = smem_u32(&sm.ev[0]);
-        EvRegs pre = { 0.f, 1.f, 0.f, 0.f };
-        float* gcol = acol + j0;                                // this thread's 8 slots of column i-1 (group-major)
-        const unsigned lane0 = (lane == 0) ? 1u : 0u;
-
-        auto column = [&](auto cur_tag, const unsigned i) {
-            constexpr unsigned RD = decltype(cur_tag)::value * COL_BYTES;          // column i-1
-            constexpr unsigned WR = (1 - decltype(cur_tag)::value) * COL_BYTES;    // column i
-            if constexpr (decltype(cur_tag)::value == 0)   // i is odd in this half: the staging points are odd
+        const unsigned raw_b = smem_u32(&sm.raw[0][t & (CH - 1)]);
+        auto column = [&](auto par_tag, const unsigned i) {
+            constexpr unsigned RD = decltype(par_tag)::value;       // i & 1: buffer holding column i's candidates
+            if constexpr (RD == 1)   // i is odd: the staging points are odd
             {
                 const unsigned ic = i & (CH - 1);
-                if (ic == 1 && t < CH) pre = ev_load(a, off, (i - 1) + CH + t, n);
-                if (ic == 17 && t < CH) sm.ev[((((i - 1) / CH) + 1) & 1) * CH + t] = ev_slot(ev_pack(pre, J.drift));
+                // next chunk of events: HBM -> shared by cp.async (no registers held across columns), converted to
+                // the staged form 16 columns later by the thread that requested it
+                if (ic == 1 && t < CH) ev_request(a, raw_b, off, (i - 1) + CH + t, n);
+                if (ic == 17 && t < CH)
+                    sm.ev[((((i - 1) / CH) + 1) & 1) * CH + t] = ev_slot(ev_pack(ev_collect(a, sm.raw, t, (i - 17) + CH + t, n), J.drift));
             }
-            // ---- part 1: column i-1 is complete.  Predecessor loads first, then the rest of this event's emission.
-            float c2[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) c2[k] = lds32(two_b + RD + (k << 10));
-            // these 8 values are slots 8t..8t+7 of column i-1 in the slab's group-major layout: stream them out now
-            if (keep) st_cs_v8(gcol, c2);
-            gcol += NC_N_STATES;
-            float2 o[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) o[b] = lds64(one_b + RD + (b << 12) + ((b >> 1) << 6));
+            // ---- part 1: every candidate of column i is published.  Loads first, then the rest of this event's
+            // emission (pairs 2,3) in their latency shadow.
+            const float4 c2a = lds128(rd_x2 + RD * X2_BUF), c2b = lds128(rd_x2 + RD * X2_BUF + 16);
+            const float4 c1a = lds128(rd_x1 + RD * X1_BUF), c1b = lds128(rd_x1 + RD * X1_BUF + 16);
             const float4 ev_i = lds128(ev_b + ((i & (2 * CH - 1)) << 4));
             f2 e23[2];
             {
@@ -347,61 +433,40 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
                 e23[0] = emission2(P[2], lds64p(prm_nls + 2 * PRM_PAIR), lds64p(prm_c1h + 2 * PRM_PAIR), E, M2, NH);
                 e23[1] = emission2(P[3], lds64p(prm_nls + 3 * PRM_PAIR), lds64p(prm_c1h + 3 * PRM_PAIR), E, M2, NH);
             }
-            // two-step class: this thread's 8 of the group's 16 predecessors, the partner (lane ^ 1) holds the rest
-            const float m2 = fmaxf(fmaxf(fmaxf(c2[0], c2[1]), fmaxf(c2[2], c2[3])), fmaxf(fmaxf(c2[4], c2[5]), fmaxf(c2[6], c2[7])));
-            const float m2o = __shfl_xor_sync(0xffffffffu, m2, 1);
-            // one-step class for h = 2t and 2t+1
-            const float v1a = __fadd_rn(w1a, fmaxf(fmaxf(o[0].x, o[1].x), fmaxf(o[2].x, o[3].x)));
-            const float v1b = __fadd_rn(w1b, fmaxf(fmaxf(o[0].y, o[1].y), fmaxf(o[2].y, o[3].y)));
             f2 vs[SPT / 2];
 #pragma unroll
             for (int k = 0; k < SPT / 2; ++k) vs[k] = add2(ws[k], a_own[k]);   // self candidates
-            const float v2 = __fadd_rn(w2, fmaxf(m2, m2o));
-            const float va = fmaxf(v1a, v2), vb = fmaxf(v1b, v2);
-            a_own[0] = add2(pk(fmaxf(lo_of(vs[0]), va), fmaxf(hi_of(vs[0]), va)), e01[0]);
-            a_own[1] = add2(pk(fmaxf(lo_of(vs[1]), va), fmaxf(hi_of(vs[1]), va)), e01[1]);
-            a_own[2] = add2(pk(fmaxf(lo_of(vs[2]), vb), fmaxf(hi_of(vs[2]), vb)), e23[0]);
-            a_own[3] = add2(pk(fmaxf(lo_of(vs[3]), vb), fmaxf(hi_of(vs[3]), vb)), e23[1]);
-            float an[SPT];
-#pragma unroll
-            for (int k = 0; k < SPT / 2; ++k) { an[2 * k] = lo_of(a_own[k]); an[2 * k + 1] = hi_of(a_own[k]); }
-            sts128(wr_lo + WR, an[0], an[1], an[2], an[3]);
-            sts128(wr_hi + WR, an[4], an[5], an[6], an[7]);
-            // ---- column i is published; part 2 runs in the barrier's shadow: pairs 0,1 of event i+1
-            __syncwarp();
-            mbar_arrive_if(bar, lane0);
+            a_own[0] = add2(pk(max3(c2a.x, c1a.x, lo_of(vs[0])), max3(c2a.y, c1a.y, hi_of(vs[0]))), e01[0]);
+            a_own[1] = add2(pk(max3(c2a.z, c1a.z, lo_of(vs[1])), max3(c2a.w, c1a.w, hi_of(vs[1]))), e01[1]);
+            a_own[2] = add2(pk(max3(c2b.x, c1b.x, lo_of(vs[2])), max3(c2b.y, c1b.y, hi_of(vs[2]))), e23[0]);
+            a_own[3] = add2(pk(max3(c2b.z, c1b.z, lo_of(vs[3])), max3(c2b.w, c1b.w, hi_of(vs[3]))), e23[1]);
+            // ---- column i is complete in registers: publish column i+1's candidates into the other buffer
+            publish(std::integral_constant< unsigned, 1 - RD >{});
+            // ---- part 2 runs in the barrier's shadow: pairs 0,1 of event i+1
             {
                 const EvPairs E = ev_pairs(lds128(ev_b + (((i + 1) & (2 * CH - 1)) << 4)));
                 e01[0] = emission2(P[0], lds64p(prm_nls), lds64p(prm_c1h), E, M2, NH);
                 e01[1] = emission2(P[1], lds64p(prm_nls + PRM_PAIR), lds64p(prm_c1h + PRM_PAIR), E, M2, NH);
             }
-            mbar_wait_u32(bar, decltype(cur_tag)::value);
+            mbar_wait_u32(bar, RD);   // phase i
         };
         {
             unsigned i = 1;
             for (; i + 1 < n; i += 2)
             {
-                column(std::integral_constant< int, 0 >{}, i);
-                column(std::integral_constant< int, 1 >{}, i + 1);
+                column(std::integral_constant< unsigned, 1 >{}, i);
+                column(std::integral_constant< unsigned, 0 >{}, i + 1);
             }
-            if (i < n)
+            if (i < n) column(std::integral_constant< unsigned, 1 >{}, i);   // n even: n phases in all
+            else
             {
-                column(std::integral_constant< int, 0 >{}, i);
-                // an empty phase keeps the number of barrier phases per job even (parity == buffer index)
+                // n odd: an empty phase keeps the number of barrier phases per job even (parity == i & 1)
                 __syncwarp();
                 mbar_arrive_if(bar, lane0);
                 mbar_wait_u32(bar, 1);
             }
         }
-        if (keep)
-        {
-            // the last column (buffer (n-1) & 1), in the same group-major order
-            float c2[8];
-            const unsigned RDL = ((n - 1) & 1u) * COL_BYTES;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) c2[k] = lds32(two_b + RDL + (k << 10));
-            st_cs_v8(gcol, c2);
-        }
+        // (the publish of the last column streamed it to the slab; its candidates are never read)
         float a_fin[SPT];
 #pragma unroll
         for (int k = 0; k < SPT / 2; ++k) { a_fin[2 * k] = lo_of(a_own[k]); a_fin[2 * k + 1] = hi_of(a_own[k]); }
@@ -409,10 +474,13 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
         // ---------------- fill_state_seq: argmax over the last column, strict '>' ascending j (Viterbi.hpp:123-133)
         {
             float bv = a_fin[0];
-            int bj = j0;
+            int bj = (int)own_state(T, half, 0);
 #pragma unroll
-            for (int k = 1; k < SPT; ++k)
-                if (a_fin[k] > bv) { bv = a_fin[k]; bj = j0 + k; }
+            for (int k = 1; k < SPT; ++k)   // own states do not ascend with k: ties go to the lower index explicitly
+            {
+                const int jk = (int)own_state(T, half, k);
+                if (a_fin[k] > bv || (a_fin[k] == bv && jk < bj)) { bv = a_fin[k]; bj = jk; }
+            }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1)
             {
@@ -427,7 +495,7 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
                 float fv = sm.red_v[0];
                 int fj = sm.red_j[0];
                 for (int w = 1; w < THREADS / 32; ++w)
-                    if (sm.red_v[w] > fv) { fv = sm.red_v[w]; fj = sm.red_j[w]; }
+                    if (sm.red_v[w] > fv || (sm.red_v[w] == fv && sm.red_j[w] < fj)) { fv = sm.red_v[w]; fj = sm.red_j[w]; }
                 sm.final_state = fj;
                 a.path_logprob[job_idx] = fv;
             }
