@@ -32,6 +32,10 @@
 
 #include <type_traits>
 
+#ifndef NC_EXP
+#define NC_EXP 0   // timing experiments (tools/build_variants.sh); anything but 0 is not a product build
+#endif
+
 namespace nc {
 
 using namespace vit;
@@ -398,21 +402,46 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
             for (int k = 0; k < SPT / 2; ++k)
                 a_own[k] = add2(emission2(P[k], sm.prm[0][k][t], sm.prm[1][k][t], E, M2, NH), nlog_n);
         }
-        // candidates of column 1 -> buffer 1 (phase 0 of this job); then, in the barrier's shadow, the emission of
-        // event 1 for state pairs 0,1 (the loop keeps computing them one step ahead)
-        publish(std::integral_constant< unsigned, 1 >{});
-        f2 e01[2];
-        {
-            const EvPairs E = ev_pairs(sm.ev[1]);
-            e01[0] = emission2(P[0], sm.prm[0][0][t], sm.prm[1][0][t], E, M2, NH);
-            e01[1] = emission2(P[1], sm.prm[0][1][t], sm.prm[1][1][t], E, M2, NH);
-        }
+        // emission of one event for all four state pairs of this thread
+        auto emit_all = [&](f2 (&e)[SPT / 2], const unsigned ev_index) {
+            const float4 ev_i = lds128(ev_b + ((ev_index & (2 * CH - 1)) << 4));
+#if NC_EXP == 4
+            e[0] = pk(ev_i.x, ev_i.y); e[1] = pk(ev_i.z, ev_i.w); e[2] = pk(ev_i.y, ev_i.x); e[3] = pk(ev_i.w, ev_i.z);
+#else
+            const EvPairs E = ev_pairs(ev_i);
+#pragma unroll
+            for (int k = 0; k < SPT / 2; ++k)
+                e[k] = emission2(P[k], lds64p(prm_nls + k * PRM_PAIR), lds64p(prm_c1h + k * PRM_PAIR), E, M2, NH);
+#endif
+        };
+
+        // ---------------- columns 1..n-1 (Viterbi.hpp:72-96), max only.
+        // Per column a warp has two kinds of work: the emission of its states (FMA pipe: 76 packed operations per
+        // thread, the bulk of the kernel's arithmetic, no dependence on other threads) and the recursion step
+        // (candidate loads -> max -> class maxima -> shuffle -> publish -> column barrier: few instructions, a long
+        // dependent chain).  Run by all warps in the same order the two do not overlap -- every warp of a
+        // sub-partition fights for the FMA pipe at the same time and then waits out the chain at the same time
+        // (measured: recursion alone 427 cycles/column, emission alone ~730, together 1121).  So the warps of each
+        // sub-partition are split into two groups that run the SAME computation in a different order:
+        //   group A (early):  emission of event i  ->  recursion step i  ->  barrier
+        //   group B (late):   recursion step i  ->  arrive  ->  emission of event i+1 in the barrier's shadow
+        // While A computes emissions B walks its chain, and while A walks its chain B computes emissions.
+        const unsigned raw_b = smem_u32(&sm.raw[0][t & (CH - 1)]);
+#if NC_EXP == 6
+        const bool group_a = ((warp >> 2) & 1) == 0;   // staggered: warps w, w+4, w+8, w+12 share a sub-partition
+#elif NC_EXP == 7
+        const bool group_a = true;
+#else
+        const bool group_a = false;
+#endif
+        f2 ec[SPT / 2];                                // group B: emission carried across the barrier
+        publish(std::integral_constant< unsigned, 1 >{});   // candidates of column 1 -> buffer 1 (phase 0)
+        if (!group_a) emit_all(ec, 1);
         mbar_wait_u32(bar, 0);
 
-        // ---------------- columns 1..n-1 (Viterbi.hpp:72-96), max only
-        const unsigned raw_b = smem_u32(&sm.raw[0][t & (CH - 1)]);
-        auto column = [&](auto par_tag, const unsigned i) {
+        auto column = [&](auto par_tag, auto ga_tag, const unsigned i) {
             constexpr unsigned RD = decltype(par_tag)::value;       // i & 1: buffer holding column i's candidates
+            constexpr bool GA = decltype(ga_tag)::value;
             if constexpr (RD == 1)   // i is odd: the staging points are odd
             {
                 const unsigned ic = i & (CH - 1);
@@ -422,42 +451,38 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
                 if (ic == 17 && t < CH)
                     sm.ev[((((i - 1) / CH) + 1) & 1) * CH + t] = ev_slot(ev_pack(ev_collect(a, sm.raw, t, (i - 17) + CH + t, n), J.drift));
             }
-            // ---- part 1: every candidate of column i is published.  Loads first, then the rest of this event's
-            // emission (pairs 2,3) in their latency shadow.
+            // every candidate of column i is published
             const float4 c2a = lds128(rd_x2 + RD * X2_BUF), c2b = lds128(rd_x2 + RD * X2_BUF + 16);
             const float4 c1a = lds128(rd_x1 + RD * X1_BUF), c1b = lds128(rd_x1 + RD * X1_BUF + 16);
-            const float4 ev_i = lds128(ev_b + ((i & (2 * CH - 1)) << 4));
-            f2 e23[2];
+            f2 e[SPT / 2];
+            if constexpr (GA) emit_all(e, i);
+            else
             {
-                const EvPairs E = ev_pairs(ev_i);
-                e23[0] = emission2(P[2], lds64p(prm_nls + 2 * PRM_PAIR), lds64p(prm_c1h + 2 * PRM_PAIR), E, M2, NH);
-                e23[1] = emission2(P[3], lds64p(prm_nls + 3 * PRM_PAIR), lds64p(prm_c1h + 3 * PRM_PAIR), E, M2, NH);
+#pragma unroll
+                for (int k = 0; k < SPT / 2; ++k) e[k] = ec[k];
             }
             f2 vs[SPT / 2];
 #pragma unroll
             for (int k = 0; k < SPT / 2; ++k) vs[k] = add2(ws[k], a_own[k]);   // self candidates
-            a_own[0] = add2(pk(max3(c2a.x, c1a.x, lo_of(vs[0])), max3(c2a.y, c1a.y, hi_of(vs[0]))), e01[0]);
-            a_own[1] = add2(pk(max3(c2a.z, c1a.z, lo_of(vs[1])), max3(c2a.w, c1a.w, hi_of(vs[1]))), e01[1]);
-            a_own[2] = add2(pk(max3(c2b.x, c1b.x, lo_of(vs[2])), max3(c2b.y, c1b.y, hi_of(vs[2]))), e23[0]);
-            a_own[3] = add2(pk(max3(c2b.z, c1b.z, lo_of(vs[3])), max3(c2b.w, c1b.w, hi_of(vs[3]))), e23[1]);
-            // ---- column i is complete in registers: publish column i+1's candidates into the other buffer
+            a_own[0] = add2(pk(max3(c2a.x, c1a.x, lo_of(vs[0])), max3(c2a.y, c1a.y, hi_of(vs[0]))), e[0]);
+            a_own[1] = add2(pk(max3(c2a.z, c1a.z, lo_of(vs[1])), max3(c2a.w, c1a.w, hi_of(vs[1]))), e[1]);
+            a_own[2] = add2(pk(max3(c2b.x, c1b.x, lo_of(vs[2])), max3(c2b.y, c1b.y, hi_of(vs[2]))), e[2]);
+            a_own[3] = add2(pk(max3(c2b.z, c1b.z, lo_of(vs[3])), max3(c2b.w, c1b.w, hi_of(vs[3]))), e[3]);
+            // column i is complete in registers: publish column i+1's candidates into the other buffer
             publish(std::integral_constant< unsigned, 1 - RD >{});
-            // ---- part 2 runs in the barrier's shadow: pairs 0,1 of event i+1
-            {
-                const EvPairs E = ev_pairs(lds128(ev_b + (((i + 1) & (2 * CH - 1)) << 4)));
-                e01[0] = emission2(P[0], lds64p(prm_nls), lds64p(prm_c1h), E, M2, NH);
-                e01[1] = emission2(P[1], lds64p(prm_nls + PRM_PAIR), lds64p(prm_c1h + PRM_PAIR), E, M2, NH);
-            }
+            if constexpr (!GA) emit_all(ec, i + 1);
+#if NC_EXP != 1
             mbar_wait_u32(bar, RD);   // phase i
+#endif
         };
-        {
+        auto columns = [&](auto ga_tag) {
             unsigned i = 1;
             for (; i + 1 < n; i += 2)
             {
-                column(std::integral_constant< unsigned, 1 >{}, i);
-                column(std::integral_constant< unsigned, 0 >{}, i + 1);
+                column(std::integral_constant< unsigned, 1 >{}, ga_tag, i);
+                column(std::integral_constant< unsigned, 0 >{}, ga_tag, i + 1);
             }
-            if (i < n) column(std::integral_constant< unsigned, 1 >{}, i);   // n even: n phases in all
+            if (i < n) column(std::integral_constant< unsigned, 1 >{}, ga_tag, i);   // n even: n phases in all
             else
             {
                 // n odd: an empty phase keeps the number of barrier phases per job even (parity == i & 1)
@@ -465,7 +490,9 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
                 mbar_arrive_if(bar, lane0);
                 mbar_wait_u32(bar, 1);
             }
-        }
+        };
+        if (group_a) columns(std::true_type{});
+        else columns(std::false_type{});
         // (the publish of the last column streamed it to the slab; its candidates are never read)
         float a_fin[SPT];
 #pragma unroll

@@ -19,6 +19,11 @@
 #define OP_LOP(i) asm volatile("xor.b32 %0, %0, %1;" : "+r"(u[i]) : "r"(k1));
 #define OP_IMAD(i) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(k1), "r"(k2));
 #define OP_FFMA2(i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(w[i]) : "l"(d1), "l"(d2));
+#define OP_FFMA2R(i) asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(w[i]) : "l"(w[(i + 1) & 7]), "l"(w[(i + 2) & 7]), "l"(w[(i + 3) & 7]));
+#define OP_FADD2R(i) asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(w[i]) : "l"(w[(i + 1) & 7]), "l"(w[(i + 2) & 7]));
+#define OP_MIX_FFMA2R_FMNMX3(i) OP_FFMA2R(i) asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(y[i]) : "f"(c2), "f"(c1));
+#define OP_MIX_FFMA2R_LDS128(i) OP_FFMA2R(i) OP_LDS128(i)
+#define OP_MIX_FADD2_FMNMX(i) OP_FADD2(i) asm volatile("max.f32 %0, %0, %1;" : "+f"(y[i]) : "f"(c2));
 #define OP_FADD2(i) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[i]) : "l"(d1));
 #define OP_FMUL2(i) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(w[i]) : "l"(d1));
 #define OP_LDS32(i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[i]) : "r"(sa + 128 * i));
@@ -89,6 +94,11 @@ DEFK(imad, 1, OP_IMAD)
 DEFK(ffma2, 1, OP_FFMA2)
 DEFK(fadd2, 1, OP_FADD2)
 DEFK(fmul2, 1, OP_FMUL2)
+DEFK(ffma2r, 1, OP_FFMA2R)
+DEFK(fadd2r, 1, OP_FADD2R)
+DEFK(mix_ffma2r_fmnmx3, 2, OP_MIX_FFMA2R_FMNMX3)
+DEFK(mix_ffma2r_lds128, 2, OP_MIX_FFMA2R_LDS128)
+DEFK(mix_fadd2_fmnmx, 2, OP_MIX_FADD2_FMNMX)
 DEFK(lds32, 1, OP_LDS32)
 DEFK(lds64, 1, OP_LDS64)
 DEFK(lds128, 1, OP_LDS128)
@@ -118,6 +128,8 @@ int main()
         run_fmnmx(nw, out, cyc, in); run_fmnmx3(nw, out, cyc, in); run_setsel(nw, out, cyc, in);
         run_iadd(nw, out, cyc, in); run_lop(nw, out, cyc, in); run_imad(nw, out, cyc, in);
         run_ffma2(nw, out, cyc, in); run_fadd2(nw, out, cyc, in); run_fmul2(nw, out, cyc, in);
+        run_ffma2r(nw, out, cyc, in); run_fadd2r(nw, out, cyc, in); run_mix_ffma2r_fmnmx3(nw, out, cyc, in);
+        run_mix_ffma2r_lds128(nw, out, cyc, in); run_mix_fadd2_fmnmx(nw, out, cyc, in);
         run_lds32(nw, out, cyc, in); run_lds64(nw, out, cyc, in); run_lds128(nw, out, cyc, in);
         run_mix_fadd_fmnmx(nw, out, cyc, in); run_mix_ffma_fmnmx(nw, out, cyc, in); run_mix_2fadd_fmnmx(nw, out, cyc, in);
         run_mix_3fadd_fmnmx(nw, out, cyc, in); run_mix_ffma2_fmnmx(nw, out, cyc, in); run_mix_ffma2_fadd(nw, out, cyc, in);
