@@ -18,16 +18,29 @@
 // is therefore bit-identical to the reference's (Viterbi.hpp:78-90), and the traceback re-derives each backpointer
 // from those bits with the reference's rule: first maximum in ascending predecessor order (strict '>').
 //
-// Mapping: as viterbi_kernel -- one persistent CTA of 512 threads per SM, thread t owns states 8t..8t+7, previous
-// column double-buffered in shared memory, one mbarrier phase per column.
+// Mapping: one persistent CTA of 512 threads per SM and one job (read x model) at a time per CTA.  Thread
+// t = 2 T + half owns the 8 states (b << 10) | (b' << 8) | T with b = 0..3, b' = 2 half + {0, 1}: half of the 16
+// states that share their low 8 bits.  These are exactly the two-step predecessors of group G = T and, per b', the
+// one-step predecessors of group H = (b' << 8) | T, so the class maxima are taken on the thread's OWN registers
+// (one shuffle with lane ^ 1 completes the two-step group) and only the weighted class candidates -- 5 KiB per
+// column instead of the 16 KiB column plus 32 KiB of predecessor reads -- cross shared memory (see SmemA).  One
+// mbarrier phase per column; the loop is unrolled by two so buffer and barrier parity are compile-time constants and
+// every shared-memory access is `base register + immediate`.
 //
-// What binds (tools/ubench/emis.cu, profiles/): the fused emission alone keeps the FMA pipe busy ~730 cycles per
-// column and SM sub-partition, everything else must hide behind it.  So (1) the loop body carries no integer
-// arithmetic on the FMA pipe (IMAD runs there at half rate): every shared-memory access is `base register +
-// immediate`, the loop is unrolled by two so buffer and barrier parity are compile-time constants; (2) the emission
-// is split: state pairs 2,3 of event i are computed next to the predecessor loads / max tree / shuffle of column i
-// (filling that chain's latency bubbles), pairs 0,1 of event i+1 between the barrier arrive and the barrier wait
-// (filling the barrier bubble); (3) the emission runs as packed FADD2/FMUL2/FFMA2 to halve its issue slots.
+// What binds (tools/ubench, tools/vit_diag.py, profiles/r1_viterbi_alpha_experiments.md).  Measured per column and
+// SM sub-partition (4 warps): recursion alone 427 cycles, emission alone ~730, together 1076 (no stores) / 1111
+// (with stores) -- they add up, in every ordering tried, because both draw on the same resource: register-file
+// operand bandwidth.  tools/ubench: an FFMA2 with three distinct 64-bit register operands issues every 3.2 cycles,
+// a two-operand FADD2/FMUL2 every 2.2-2.4, a scalar FFMA with three distinct registers every 1.6, i.e. ~2 32-bit
+// operand reads per cycle and lane.  The emission reads 79 operands per state pair (19 packed operations, two
+// Markstein divisions), the recursion ~92 per thread: ~404 reads = ~202 cycles per warp and column, 808 per
+// sub-partition, against 1076-1111 achieved.  Dropping the column barrier's wait buys 7 % (NC_EXP=1), the HBM store
+// of the column costs 3 %.  Consequences kept in the code: (1) packed FADD2/FMUL2/FFMA2 (same operand traffic as
+// scalar, half the issue slots); (2) the whole emission of event i+1 runs between the barrier arrive and the
+// barrier wait of column i -- 11 % faster than splitting it around the recursion step, and faster than staggering
+// the warps of a sub-partition (NC_EXP=6) or computing it ahead of the step (NC_EXP=7); (3) no integer arithmetic
+// in the loop (IMAD shares the FMA pipe at half rate); (4) events are staged by cp.async so no registers are held
+// across columns.  Under sustained load the GPU runs into its 1000 W power cap (SM clock 1875 of 1965 MHz).
 #include "nc_vit_common.cuh"
 
 #include <type_traits>
@@ -416,16 +429,13 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
         };
 
         // ---------------- columns 1..n-1 (Viterbi.hpp:72-96), max only.
-        // Per column a warp has two kinds of work: the emission of its states (FMA pipe: 76 packed operations per
-        // thread, the bulk of the kernel's arithmetic, no dependence on other threads) and the recursion step
-        // (candidate loads -> max -> class maxima -> shuffle -> publish -> column barrier: few instructions, a long
-        // dependent chain).  Run by all warps in the same order the two do not overlap -- every warp of a
-        // sub-partition fights for the FMA pipe at the same time and then waits out the chain at the same time
-        // (measured: recursion alone 427 cycles/column, emission alone ~730, together 1121).  So the warps of each
-        // sub-partition are split into two groups that run the SAME computation in a different order:
-        //   group A (early):  emission of event i  ->  recursion step i  ->  barrier
-        //   group B (late):   recursion step i  ->  arrive  ->  emission of event i+1 in the barrier's shadow
-        // While A computes emissions B walks its chain, and while A walks its chain B computes emissions.
+        // Per column a warp has two kinds of work: the emission of its states (76 packed operations per thread, the
+        // bulk of the kernel's arithmetic, no dependence on other threads) and the recursion step (candidate loads
+        // -> max -> class maxima -> shuffle -> publish -> column barrier).  Two orders of the same computation:
+        //   A (early):  emission of event i  ->  recursion step i  ->  barrier
+        //   B (late):   recursion step i  ->  arrive  ->  emission of event i+1 in the barrier's shadow
+        // B for every warp is the product build (1111 cycles/column); A for every warp (NC_EXP=7) measures 1368,
+        // two warps of each sub-partition on A and two on B (NC_EXP=6) 1320: see the file header.
         const unsigned raw_b = smem_u32(&sm.raw[0][t & (CH - 1)]);
 #if NC_EXP == 6
         const bool group_a = ((warp >> 2) & 1) == 0;   // staggered: warps w, w+4, w+8, w+12 share a sub-partition
