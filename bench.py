@@ -10,10 +10,15 @@ Under torchrun (N > 1) every rank decodes its own R reads on its own GPU (reads 
 no data-path collective): scaling = "weak", value = all ranks' events / max-over-ranks time.
 
 JSON line keys beyond the base contract:
-  roofline      HBM view of the dominant kernel (viterbi_kernel): algorithmic bytes = 4112 B/event
-                (4096 B backpointers + 12 B event + 1 B traceback read + 3 B state/move)
-  roofline_fp32 the roofline that actually binds (FP32 issue): 245,600 FP32 op/event
-                against 148 SMs x 128 lanes x SM clock measured under load
+  roofline      HBM view of the dominant kernel (viterbi_alpha_kernel): algorithmic bytes = 4112 B/event
+                (4096 B backpointers + 12 B event + 1 B traceback read + 3 B state/move) over the
+                kernel's own launch duration (CUDA events on the context's stream around each launch);
+                `traffic` = DRAM bytes per launch from the committed ncu capture (the kernel streams the alpha
+                columns, 16 KiB/event, by design: DESIGN.md K1a)
+  roofline_fp32 algorithmic FP32 work: 245,600 FP32 op/event against 148 SMs x 128 lanes x
+                SM clock measured under load (> 1: class sharing removes 2/3 of the edge operations)
+  roofline_rf   what binds (profiles/r1_viterbi_alpha_experiments.md): register-file operand reads,
+                404 per thread and column, against the measured 2 reads per cycle and lane
   cpu_baseline  the reference's own Viterbi (oracle/_ref, kind "reference"; the C port otherwise)
                 on a bounded sample of the same reads on this box's host cores
   e2e           same metric through nc_viterbi_packed with pinned HOST buffers: H2D of the events
@@ -34,6 +39,9 @@ sys.path.insert(0, ROOT)
 
 HBM_BYTES_PER_EVENT = 4112
 FP32_OPS_PER_EVENT = 245600
+RF_READS_PER_EVENT = 404 * 512  # operand reads per thread and column x threads (nc_viterbi_alpha.cu header)
+# dram__bytes_read.sum + dram__bytes_write.sum per event of viterbi_alpha_kernel, from the committed capture
+NCU_DRAM_BYTES_PER_EVENT = {"viterbi_alpha_kernel": 16942.0, "source": "profiles/r1_ncu_viterbi_alpha_summary.md"}
 MODEL = "r73.t.006.ont.model"
 
 
@@ -229,9 +237,11 @@ def main():
     e0.record(stream)
     path = None
     launches = 0
+    kernel_ms = []
     for _ in range(args.steps):
         path = step_device()
         launches += ctx.last_launches()
+        kernel_ms.append(ctx.last_kernel_ms())   # CUDA events on the context's stream around the kernel launch
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -276,7 +286,10 @@ def main():
         value = world * total / (ms_per_step * 1e-3)
         hbm_peak, peak_kind = peaks()
         per_gpu_evs = total / (ms_per_step * 1e-3)
-        ach_gbs = per_gpu_evs * HBM_BYTES_PER_EVENT / 1e9
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        ach_gbs = total * HBM_BYTES_PER_EVENT / (k_ms * 1e-3) / 1e9
+        kname = "viterbi_kernel" if args.vit_mode == "backpointer" else "viterbi_alpha_kernel"
+        traffic = NCU_DRAM_BYTES_PER_EVENT.get(kname)
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         fp32_peak = info["n_sms"] * 128 * sm_mhz * 1e6 / 1e12  # T FP32 instr/s (non-FMA issue)
         line = {
@@ -291,14 +304,22 @@ def main():
             "clocks": clocks,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind,
-                         "kernel": "viterbi_kernel" if args.vit_mode == "backpointer" else "viterbi_alpha_kernel",
+                         "frac": ach_gbs / hbm_peak, "traffic": traffic * total if traffic else None,
+                         "traffic_source": NCU_DRAM_BYTES_PER_EVENT["source"] if traffic else None,
+                         "peak_kind": peak_kind, "kernel": kname, "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": HBM_BYTES_PER_EVENT * total,
                          "algorithmic_bytes_per_event": HBM_BYTES_PER_EVENT},
             "roofline_fp32": {"bound": "fp32_issue", "achieved": per_gpu_evs * FP32_OPS_PER_EVENT / 1e12,
                               "peak": fp32_peak, "unit": "Tinstr/s", "frac": per_gpu_evs * FP32_OPS_PER_EVENT / 1e12 / fp32_peak,
                               "algorithmic_ops_per_event": FP32_OPS_PER_EVENT,
                               "peak_kind": f"{info['n_sms']} SMs x 128 lanes x {sm_mhz:.0f} MHz under load"},
         }
+        if args.vit_mode != "backpointer":
+            rf_peak = info["n_sms"] * 128 * 2 * sm_mhz * 1e6 / 1e12
+            line["roofline_rf"] = {"bound": "register_operand_reads", "achieved": per_gpu_evs * RF_READS_PER_EVENT / 1e12,
+                                   "peak": rf_peak, "unit": "Treads/s", "frac": per_gpu_evs * RF_READS_PER_EVENT / 1e12 / rf_peak,
+                                   "reads_per_event": RF_READS_PER_EVENT,
+                                   "peak_kind": f"{info['n_sms']} SMs x 128 lanes x 2 reads/clk (tools/ubench) x {sm_mhz:.0f} MHz"}
         if e2e:
             line["e2e"] = {"value": world * total * args.steps / e2e[0], "unit": "events/s",
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],

@@ -48,10 +48,81 @@ __device__ __forceinline__ float flogsum(float a, float b, const float* __restri
     return plain ? mx : r;
 }
 
+// Sequential float sum of T[0..4095] (all terms >= 0) with the bits of the serial loop `for j: acc += T[j]`.
+// Per 64 terms: the lanes screen their terms against the running sum (a term below acc * 2^-25 is below half an
+// ulp of acc and of every later value of acc; +0 never changes it), the survivors are compacted in order into a
+// small per-warp list, and the dependent chain of additions runs over that list from shared memory: no shuffle and
+// no branch per term inside the chain (the list is padded with +0 to a multiple of four).
+constexpr int FOLD_LIST = 80;
+__device__ __forceinline__ float fold_sum_in_order(const float* __restrict__ T, float* __restrict__ lst, const int lane)
+{
+    float acc = 0.0f;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < (int)NC_N_STATES; base += 64)
+    {
+        const float x0 = T[base + lane];
+        const float x1 = T[base + 32 + lane];
+        const float thr = __fmul_rn(acc, 2.98023223876953125e-8f);  // 2^-25
+        const bool l0 = !(x0 < thr) && !(x0 == 0.0f);               // NaN stays live, as in the serial loop
+        const bool l1 = !(x1 < thr) && !(x1 == 0.0f);
+        const unsigned m0 = __ballot_sync(0xffffffffu, l0);
+        const unsigned m1 = __ballot_sync(0xffffffffu, l1);
+        const int c0 = __popc(m0), cnt = c0 + __popc(m1);
+        if (cnt == 0) continue;
+        if (l0) lst[__popc(m0 & lt)] = x0;
+        if (l1) lst[c0 + __popc(m1 & lt)] = x1;
+        if (lane < 8) lst[cnt + lane] = 0.0f;
+        __syncwarp();
+        const float4* l4 = reinterpret_cast< const float4* >(lst);
+        float4 v = l4[0];
+        for (int k = 0; k < cnt; k += 4)
+        {
+            const float4 nv = l4[(k >> 2) + 1];   // one ahead: the load overlaps the four dependent additions
+            acc = __fadd_rn(acc, v.x);
+            acc = __fadd_rn(acc, v.y);
+            acc = __fadd_rn(acc, v.z);
+            acc = __fadd_rn(acc, v.w);
+            v = nv;
+        }
+        __syncwarp();
+    }
+    return acc;
+}
+
+// The log-space twin: acc = p7_FLogsum(acc, x_k) over k = 0..n-1 in order, n a multiple of 32, x_k = get(k).
+// A term with x == -inf or acc - x >= 15.999 returns acc unchanged now and for every larger acc (the running value
+// never decreases), so it is screened out; the survivors are folded from the per-warp list, padded with -inf.
+template < typename Get >
+__device__ __forceinline__ float fold_logsum_in_order(float acc, const int n, Get get, float* __restrict__ lst,
+                                                      const float* __restrict__ tbl, const int lane)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < n; base += 32)
+    {
+        const float x = get(base + lane);
+        const bool live = !((x == NC_NEG_INF) || (acc > x && __fsub_rn(acc, x) >= 15.999f));
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (m == 0) continue;
+        const int cnt = __popc(m);
+        if (live) lst[__popc(m & lt)] = x;
+        if (lane < 4) lst[cnt + lane] = NC_NEG_INF;
+        __syncwarp();
+        for (int k = 0; k < cnt; k += 2)
+        {
+            const float2 v = *reinterpret_cast< const float2* >(lst + k);
+            acc = flogsum(acc, v.x, tbl);
+            acc = flogsum(acc, v.y, tbl);
+        }
+        __syncwarp();
+    }
+    return acc;
+}
+
 struct StSmem
 {
     float tbl[16000];
     float term[3][FB_THREADS];
+    float lst[3][FOLD_LIST];
     float accs[4];
 };
 
@@ -60,6 +131,7 @@ struct FbSmem
     float tbl[16000];
     float col[2][COL_FLOATS];
     float red[FB_THREADS / 32];
+    float lst[FOLD_LIST];
     unsigned item;
 };
 
@@ -178,24 +250,24 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
                     vO[0][b] = __fadd_rn(wO[0], o.x);
                     vO[1][b] = __fadd_rn(wO[1], o.y);
                 }
-                float own[FB_SPT];
-                {
-                    const float4 o0 = *reinterpret_cast< const float4* >(A + cphys(j0));
-                    const float4 o1 = *reinterpret_cast< const float4* >(A + cphys(j0 + 4));
-                    own[0] = o0.x; own[1] = o0.y; own[2] = o0.z; own[3] = o0.w;
-                    own[4] = o1.x; own[5] = o1.y; own[6] = o1.z; own[7] = o1.w;
-                }
-                float res[FB_SPT];
-#pragma unroll
+                float* An = sm.col[cur ^ 1];
+                const float* Ei = E + (size_t)i * NC_N_STATES;
+                // one state at a time (NOT unrolled): with the 16 slots unrolled inside, an unrolled k loop makes
+                // the kernel 290 KB of SASS and every column refetches it through the instruction cache
+                // (stall_no_instruction was 5 cycles per issue).  The other warps of the two resident CTAs hide
+                // the latency of the now sequential chains.
+#pragma unroll 1
                 for (int k = 0; k < FB_SPT; ++k)
                 {
                     const int hh = k >> 2;
                     const unsigned j = j0 + k;
+                    const float own_k = A[cphys(j)];
+                    const float e_k = __ldg(Ei + j);
                     const int kO = (2 * t + hh) & 255;
                     const int kS = j & 255;
                     const bool oBefT = kO < kT, oEqT = kO == kT;
                     const bool sEqT = kS == kT, sEqO = kS == kO;
-                    const float vS = __fadd_rn(J.lut[trans_mask(j, j)], own[k]);
+                    const float vS = __fadd_rn(J.lut[trans_mask(j, j)], own_k);
                     float acc = NC_NEG_INF;
 #pragma unroll
                     for (int s = 0; s < 16; ++s)
@@ -208,7 +280,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
                             const bool dropT = (hasO && oEqT) || (hasS && sEqT);
                             const bool dropO = !hasO || (hasS && sEqO);
                             const float xT = dropT ? NC_NEG_INF : vT[s];
-                            const float xO = dropO ? NC_NEG_INF : vO[hh][s >> 2];
+                            const float xO = dropO ? NC_NEG_INF : (hh ? vO[1][s >> 2] : vO[0][s >> 2]);
                             const bool oFirst = hasO && oBefT;
                             const float first = oFirst ? xO : xT;
                             const float second = oFirst ? xT : xO;
@@ -228,17 +300,11 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
                             }
                         }
                     }
-                    res[k] = acc;
+                    An[cphys(j)] = __fadd_rn(e_k, acc);
                 }
-                const float4 e0 = *reinterpret_cast< const float4* >(E + (size_t)i * NC_N_STATES + j0);
-                const float4 e1 = *reinterpret_cast< const float4* >(E + (size_t)i * NC_N_STATES + j0 + 4);
-                const float4 a0 = make_float4(__fadd_rn(e0.x, res[0]), __fadd_rn(e0.y, res[1]), __fadd_rn(e0.z, res[2]), __fadd_rn(e0.w, res[3]));
-                const float4 a1 = make_float4(__fadd_rn(e1.x, res[4]), __fadd_rn(e1.y, res[5]), __fadd_rn(e1.z, res[6]), __fadd_rn(e1.w, res[7]));
-                float* An = sm.col[cur ^ 1];
-                *reinterpret_cast< float4* >(An + cphys(j0)) = a0;
-                *reinterpret_cast< float4* >(An + cphys(j0 + 4)) = a1;
-                *reinterpret_cast< float4* >(AL + (size_t)i * NC_N_STATES + j0) = a0;
-                *reinterpret_cast< float4* >(AL + (size_t)i * NC_N_STATES + j0 + 4) = a1;
+                // the thread's 8 new values, read back as two float4, go to the slab with vector stores
+                *reinterpret_cast< float4* >(AL + (size_t)i * NC_N_STATES + j0) = *reinterpret_cast< const float4* >(An + cphys(j0));
+                *reinterpret_cast< float4* >(AL + (size_t)i * NC_N_STATES + j0 + 4) = *reinterpret_cast< const float4* >(An + cphys(j0 + 4));
                 cur ^= 1;
                 __syncthreads();
             }
@@ -248,18 +314,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
             if (t < 32)
             {
                 const float* A = sm.col[cur];
-                float acc = NC_NEG_INF;
-                for (int base = 0; base < (int)NC_N_STATES; base += 32)
-                {
-                    const float x = A[cphys(base + lane)];
-                    unsigned live = __ballot_sync(0xffffffffu, !((x == NC_NEG_INF) || (acc > x && __fsub_rn(acc, x) >= 15.999f)));
-                    while (live)
-                    {
-                        const int b = __ffs(live) - 1;
-                        live &= live - 1;
-                        acc = flogsum(acc, __shfl_sync(0xffffffffu, x, b), tbl);
-                    }
-                }
+                const float acc = fold_logsum_in_order(NC_NEG_INF, (int)NC_N_STATES, [&](int j) { return A[cphys(j)]; }, sm.lst, tbl, lane);
                 if (lane == 0) a.log_pr_data[seq] = acc;
             }
             __syncthreads();
@@ -303,7 +358,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
                     vT[4 * v + 2] = __fadd_rn(__fadd_rn(wTb, e.z), b.z);
                     vT[4 * v + 3] = __fadd_rn(__fadd_rn(wTb, e.w), b.w);
                 }
-                float res[FB_SPT];
+                float* Bc = sm.col[cur ^ 1];
 #pragma unroll
                 for (int f = 0; f < 2; ++f)
                 {
@@ -339,7 +394,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
                         else val = oIn ? NC_NEG_INF : val;
                         L[q] = val;
                     }
-#pragma unroll
+#pragma unroll 1
                     for (int kk = 0; kk < 4; ++kk)
                     {
                         const int k = 2 * kk + f;
@@ -363,16 +418,9 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
                             acc = flogsum(acc, (q == mpos) ? vS : L[q], tbl);
                         }
                         acc = flogsum(acc, pos == 2 ? vS : NC_NEG_INF, tbl);
-                        res[k] = acc;
+                        Bc[cphys(j)] = acc;
+                        BE[(size_t)i * NC_N_STATES + j] = acc;
                     }
-                }
-                float* Bc = sm.col[cur ^ 1];
-#pragma unroll
-                for (int k = 0; k < FB_SPT; ++k)
-                {
-                    const int j = t + FB_THREADS * k;
-                    Bc[cphys(j)] = res[k];
-                    BE[(size_t)i * NC_N_STATES + j] = res[k];
                 }
                 cur ^= 1;
                 __syncthreads();
@@ -391,12 +439,14 @@ size_t st_stats_smem_bytes() { return sizeof(StSmem); }
 // with p = exp(alpha + beta - logZ).  The 3x3 system built from these sums is ill-conditioned (level means are
 // 58 +- 6 pA), so the float rounding of the reference's SEQUENTIAL j = 0..4095 accumulation is visible in the trained
 // shift/scale/var at the 1e-4 level: the order is reproduced exactly.  All terms are >= 0, so the running sum never
-// decreases and a term below half an ulp of it (t < acc * 2^-25) can never change it; one warp per sum screens 32
-// terms at a time against the running sum and adds only the rest, in order -- the same float result as the serial loop.
+// decreases and a term below half an ulp of it (t < acc * 2^-25) can never change it; one warp per sum screens 64
+// terms at a time against the running sum and adds only the rest, in order -- the same float result as the serial
+// loop (fold_sum_in_order).  About a quarter of the 4096 terms survive the screen on realistic posteriors.
 __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float (*term)[NC_N_STATES] = reinterpret_cast< float (*)[NC_N_STATES] >(smem_raw);  // [6][4096]
+    float (*lst)[FOLD_LIST] = reinterpret_cast< float (*)[FOLD_LIST] >(smem_raw + 6 * NC_N_STATES * sizeof(float));  // [6][80]
     const unsigned seq = blockIdx.y;
     const FbSeq& Q = a.seqs[seq];
     const unsigned i0 = blockIdx.x * FB_EV_TILE;
@@ -445,35 +495,14 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
         __syncthreads();
         if (warp < 6)
         {
-            const float* T = term[warp];
-            float acc = 0.0f;
-            for (int base = 0; base < (int)NC_N_STATES; base += 64)
-            {
-                const float x0 = T[base + lane];
-                const float x1 = T[base + 32 + lane];
-                const float thr = __fmul_rn(acc, 2.98023223876953125e-8f);  // 2^-25
-                unsigned live0 = __ballot_sync(0xffffffffu, !(x0 < thr));
-                unsigned live1 = __ballot_sync(0xffffffffu, !(x1 < thr));
-                while (live0)
-                {
-                    const int b = __ffs(live0) - 1;
-                    live0 &= live0 - 1;
-                    acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x0, b));
-                }
-                while (live1)
-                {
-                    const int b = __ffs(live1) - 1;
-                    live1 &= live1 - 1;
-                    acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x1, b));
-                }
-            }
+            const float acc = fold_sum_in_order(term[warp], lst[warp], lane);
             if (lane == 0) a.pm_stats[(Q.ev_out + i) * 6 + warp] = acc;
         }
         __syncthreads();
     }
 }
 
-size_t pm_stats_smem_bytes() { return 6 * NC_N_STATES * sizeof(float); }
+size_t pm_stats_smem_bytes() { return 6 * NC_N_STATES * sizeof(float) + 6 * FOLD_LIST * sizeof(float); }
 
 // ------------------------------------------------------------------------------------------------
 // train_st_params' accumulators (Parameter_Trainer.hpp:434-517) for one (group, strand):
@@ -544,19 +573,9 @@ __global__ void __launch_bounds__(FB_THREADS) st_stats_kernel(const FbArgs a)
                 __syncthreads();
                 if (warp < 3)
                 {
-                    float acc = accs[warp];
-                    for (int b0 = 0; b0 < FB_THREADS; b0 += 32)
-                    {
-                        const float x = term[warp][b0 + lane];
-                        // NaN terms (log of a negative difference cannot occur: d01 <= post) are folded like the reference would
-                        unsigned live = __ballot_sync(0xffffffffu, !((x == NC_NEG_INF) || (acc > x && __fsub_rn(acc, x) >= 15.999f)));
-                        while (live)
-                        {
-                            const int b = __ffs(live) - 1;
-                            live &= live - 1;
-                            acc = flogsum(acc, __shfl_sync(0xffffffffu, x, b), tbl);
-                        }
-                    }
+                    // NaN terms (log of a negative difference cannot occur: d01 <= post) are folded like the reference would
+                    const float* Tw = term[warp];
+                    const float acc = fold_logsum_in_order(accs[warp], FB_THREADS, [&](int k) { return Tw[k]; }, ss.lst[warp], tbl, lane);
                     if (lane == 0) accs[warp] = acc;
                 }
                 __syncthreads();

@@ -225,6 +225,9 @@ int main(int argc, char** argv)
     auto worker = [&](int g) {
         try
         {
+            auto now = [] { return std::chrono::steady_clock::now(); };
+            auto secs_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration< double >(now() - t).count(); };
+            auto w0 = now();
             Pipeline p(cli.opt, cli.first_device + g);
             p.init_models();
             std::vector< Read* > mine;
@@ -233,12 +236,18 @@ int main(int argc, char** argv)
                 p.init_read_params(reads[i]);
                 mine.push_back(&reads[i]);
             }
+            const double init_s = secs_since(w0);
+            auto w1 = now();
             if (cli.opt.train) p.train_reads(mine);
+            const double train_s = secs_since(w1);
+            auto w2 = now();
             if (cli.opt.basecall) p.basecall_reads(mine);
+            const double basecall_s = secs_since(w2);
             std::ostringstream s;
             s << "gpu " << (cli.first_device + g) << ": reads=" << mine.size() << " train_rounds=" << p.train_rounds
               << " fwbw_events=" << p.fwbw_events << " train_kernel_ms=" << p.train_kernel_ms
-              << " viterbi_events=" << p.viterbi_events << " viterbi_kernel_ms=" << p.viterbi_kernel_ms;
+              << " viterbi_events=" << p.viterbi_events << " viterbi_kernel_ms=" << p.viterbi_kernel_ms
+              << " init_s=" << init_s << " train_s=" << train_s << " basecall_s=" << basecall_s;
             summaries[g] = s.str();
         }
         catch (const std::exception& e) { errors[g] = e.what(); }
