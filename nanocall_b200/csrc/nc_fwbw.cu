@@ -35,17 +35,22 @@ constexpr int COL_FLOATS = NC_N_STATES + 4 * (NC_N_STATES >> COL_PAD_SHIFT);  //
 
 __device__ __forceinline__ int cphys(int n) { return n + ((n >> COL_PAD_SHIFT) << 2); }
 
-// p7_FLogsum (logsum.hpp:141-154)
+// p7_FLogsum (logsum.hpp:141-154): max + tbl[(int)((max - min) * 1000.f)], or max when min == -inf or
+// max - min >= 15.999f.  Same bits with 9 instructions instead of 14 (the kernels are bound by the ALU pipe, where
+// FSETP/FSEL/SEL run at half rate):
+//   * max - min == |a - b| exactly (rounding is symmetric), used as an operand modifier: no min is formed;
+//   * min == -inf implies |a - b| == +inf >= 15.999f, so that test is subsumed; when both are -inf the
+//     difference is NaN, the comparison is false and -inf + tbl[.] == -inf == max;
+//   * the index is clamped through fminf(|a - b|, 15.999f) (15.999f * 1000.f == 15999.f): in range without a select,
+//     and only changed where the result is discarded.
+// NaN inputs (which the reference only meets on invalid events) are not reproduced.
 __device__ __forceinline__ float flogsum(float a, float b, const float* __restrict__ tbl)
 {
-    const float mx = (a > b) ? a : b;
-    const float mn = (a < b) ? a : b;
-    const float d = __fsub_rn(mx, mn);
-    const bool plain = (mn == NC_NEG_INF) || (d >= 15.999f);
-    int idx = (int)__fmul_rn(d, 1000.0f);
-    idx = plain ? 0 : idx;
+    const float d = fabsf(__fsub_rn(a, b));
+    const float mx = fmaxf(a, b);
+    const int idx = __float2int_rz(__fmul_rn(fminf(d, 15.999f), 1000.0f));
     const float r = __fadd_rn(mx, tbl[idx]);
-    return plain ? mx : r;
+    return (d >= 15.999f) ? mx : r;
 }
 
 // Sequential float sum of T[0..4095] (all terms >= 0) with the bits of the serial loop `for j: acc += T[j]`.
