@@ -53,43 +53,30 @@ __device__ __forceinline__ float flogsum(float a, float b, const float* __restri
     return (d >= 15.999f) ? mx : r;
 }
 
-// Sequential float sum of T[0..4095] (all terms >= 0) with the bits of the serial loop `for j: acc += T[j]`.
-// Per 64 terms: the lanes screen their terms against the running sum (a term below acc * 2^-25 is below half an
-// ulp of acc and of every later value of acc; +0 never changes it), the survivors are compacted in order into a
-// small per-warp list, and the dependent chain of additions runs over that list from shared memory: no shuffle and
-// no branch per term inside the chain (the list is padded with +0 to a multiple of four).
+// Six sequential float sums at once: acc_s = sum over j = 0..4095 of T[s][j], s = 0..5, each the serial loop
+// `for j: acc += T[s][j]` itself -- lane s < 6 of one warp carries chain s, the terms stream from shared memory as
+// float4 one group ahead of the additions.  No screening: on training data most terms are live anyway (posteriors
+// are broad while the scaling is still off; measured ~3000 of 4096), and the chain of 4096 dependent FADDs
+// (~16 k cycles) is then the whole cost -- 5.6 k warp-instructions per event instead of ~70 k for six warps that
+// screen and compact (profiles/r1_training_kernels.md).  Rows are PM_ROW = 4096 + 4 floats apart so the six lanes'
+// float4 loads hit different banks.
 constexpr int FOLD_LIST = 80;
-__device__ __forceinline__ float fold_sum_in_order(const float* __restrict__ T, float* __restrict__ lst, const int lane)
+constexpr int ST_CHUNK = FB_THREADS - 3 * 32;   // 416 k-mers per chunk of st_stats_kernel
+constexpr int PM_ROW = NC_N_STATES + 4;
+__device__ __forceinline__ float fold_six_sums_in_order(const float* __restrict__ T, const int lane)
 {
+    const float* R = T + (lane < 6 ? lane : 0) * PM_ROW;   // lanes >= 6 shadow chain 0
     float acc = 0.0f;
-    const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < (int)NC_N_STATES; base += 64)
+    float4 v = *reinterpret_cast< const float4* >(R);
+#pragma unroll 4
+    for (int j = 0; j < (int)NC_N_STATES; j += 4)
     {
-        const float x0 = T[base + lane];
-        const float x1 = T[base + 32 + lane];
-        const float thr = __fmul_rn(acc, 2.98023223876953125e-8f);  // 2^-25
-        const bool l0 = !(x0 < thr) && !(x0 == 0.0f);               // NaN stays live, as in the serial loop
-        const bool l1 = !(x1 < thr) && !(x1 == 0.0f);
-        const unsigned m0 = __ballot_sync(0xffffffffu, l0);
-        const unsigned m1 = __ballot_sync(0xffffffffu, l1);
-        const int c0 = __popc(m0), cnt = c0 + __popc(m1);
-        if (cnt == 0) continue;
-        if (l0) lst[__popc(m0 & lt)] = x0;
-        if (l1) lst[c0 + __popc(m1 & lt)] = x1;
-        if (lane < 8) lst[cnt + lane] = 0.0f;
-        __syncwarp();
-        const float4* l4 = reinterpret_cast< const float4* >(lst);
-        float4 v = l4[0];
-        for (int k = 0; k < cnt; k += 4)
-        {
-            const float4 nv = l4[(k >> 2) + 1];   // one ahead: the load overlaps the four dependent additions
-            acc = __fadd_rn(acc, v.x);
-            acc = __fadd_rn(acc, v.y);
-            acc = __fadd_rn(acc, v.z);
-            acc = __fadd_rn(acc, v.w);
-            v = nv;
-        }
-        __syncwarp();
+        const float4 nv = *reinterpret_cast< const float4* >(R + j + 4);   // the last one reads the row's padding
+        acc = __fadd_rn(acc, v.x);
+        acc = __fadd_rn(acc, v.y);
+        acc = __fadd_rn(acc, v.z);
+        acc = __fadd_rn(acc, v.w);
+        v = nv;
     }
     return acc;
 }
@@ -126,9 +113,8 @@ __device__ __forceinline__ float fold_logsum_in_order(float acc, const int n, Ge
 struct StSmem
 {
     float tbl[16000];
-    float term[3][FB_THREADS];
+    float term[2][3][ST_CHUNK];   // two buffers: computed by warps 3..15, folded by warps 0..2
     float lst[3][FOLD_LIST];
-    float accs[4];
 };
 
 struct FbSmem
@@ -444,14 +430,12 @@ size_t st_stats_smem_bytes() { return sizeof(StSmem); }
 // with p = exp(alpha + beta - logZ).  The 3x3 system built from these sums is ill-conditioned (level means are
 // 58 +- 6 pA), so the float rounding of the reference's SEQUENTIAL j = 0..4095 accumulation is visible in the trained
 // shift/scale/var at the 1e-4 level: the order is reproduced exactly.  All terms are >= 0, so the running sum never
-// decreases and a term below half an ulp of it (t < acc * 2^-25) can never change it; one warp per sum screens 64
-// terms at a time against the running sum and adds only the rest, in order -- the same float result as the serial
-// loop (fold_sum_in_order).  About a quarter of the 4096 terms survive the screen on realistic posteriors.
+// shift/scale/var at the 1e-4 level: the order is reproduced exactly, by running the six serial loops themselves in six
+// lanes of one warp (fold_six_sums_in_order).
 __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float (*term)[NC_N_STATES] = reinterpret_cast< float (*)[NC_N_STATES] >(smem_raw);  // [6][4096]
-    float (*lst)[FOLD_LIST] = reinterpret_cast< float (*)[FOLD_LIST] >(smem_raw + 6 * NC_N_STATES * sizeof(float));  // [6][80]
+    float* term = reinterpret_cast< float* >(smem_raw);  // [6][PM_ROW]
     const unsigned seq = blockIdx.y;
     const FbSeq& Q = a.seqs[seq];
     const unsigned i0 = blockIdx.x * FB_EV_TILE;
@@ -490,104 +474,129 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
             const float ts1 = __fmul_rn(ts0, mu[k]);
             const float tl0 = __fmul_rn(p, lam[k]);
             const float tl1 = __fdiv_rn(tl0, eta[k]);
-            term[0][j0 + k] = ts0;
-            term[1][j0 + k] = ts1;
-            term[2][j0 + k] = __fmul_rn(ts1, mu[k]);
-            term[3][j0 + k] = tl0;
-            term[4][j0 + k] = tl1;
-            term[5][j0 + k] = __fdiv_rn(tl1, eta[k]);
+            term[0 * PM_ROW + j0 + k] = ts0;
+            term[1 * PM_ROW + j0 + k] = ts1;
+            term[2 * PM_ROW + j0 + k] = __fmul_rn(ts1, mu[k]);
+            term[3 * PM_ROW + j0 + k] = tl0;
+            term[4 * PM_ROW + j0 + k] = tl1;
+            term[5 * PM_ROW + j0 + k] = __fdiv_rn(tl1, eta[k]);
         }
         __syncthreads();
-        if (warp < 6)
+        if (warp == 0)
         {
-            const float acc = fold_sum_in_order(term[warp], lst[warp], lane);
-            if (lane == 0) a.pm_stats[(Q.ev_out + i) * 6 + warp] = acc;
+            const float acc = fold_six_sums_in_order(term, lane);
+            if (lane < 6) a.pm_stats[(Q.ev_out + i) * 6 + lane] = acc;
         }
         __syncthreads();
     }
 }
 
-size_t pm_stats_smem_bytes() { return 6 * NC_N_STATES * sizeof(float) + 6 * FOLD_LIST * sizeof(float); }
+size_t pm_stats_smem_bytes() { return 6 * PM_ROW * sizeof(float); }
 
 // ------------------------------------------------------------------------------------------------
 // train_st_params' accumulators (Parameter_Trainer.hpp:434-517) for one (group, strand):
 //   denom (+)= post(i,j1);  stay (+)= min(joint(j1->j1 | log p_stay), post);
 //   skip (+)= log(exp(post) - exp(min(d01, post))),  d01 = stay' (+) the 4 one-step joints with log(p_step/4)
-// over the strand's sequences in order, events i < n-1, the 2160 training k-mers in ascending order.  The terms of
-// 512 k-mers at a time are computed in parallel, then three warps fold them sequentially (screening out terms that
-// cannot change the running sum, as in the logZ fold above).
+// over the strand's sequences in order, events i < n-1, the 2160 training k-mers in ascending order.
+// Warps 3..15 compute the terms of 416 k-mers at a time into one of two buffers while warps 0..2 fold the previous
+// chunk sequentially, one accumulator each (screening out terms that cannot change the running value, as in the
+// logZ fold): the gathers and the expf/logf of chunk c+1 overlap the dependent p7_FLogsum chain of chunk c.
 __global__ void __launch_bounds__(FB_THREADS) st_stats_kernel(const FbArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StSmem& ss = *reinterpret_cast< StSmem* >(smem_raw);
     float* tbl = ss.tbl;
-    float (*term)[FB_THREADS] = ss.term;
-    float* accs = ss.accs;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int q = t; q < 16000; q += FB_THREADS) tbl[q] = a.logsum_tbl[q];
     const unsigned grp = blockIdx.x;
     const unsigned st = blockIdx.y;
     const FbGroup& G = a.groups[grp];
-    if (t < 3) accs[t] = NC_NEG_INF;
-    __syncthreads();
-    for (unsigned sq = G.seq_begin; sq < G.seq_end; ++sq)
-    {
-        const FbSeq& Q = a.seqs[sq];
-        if (Q.strand != st) continue;
+    const float log_p_stay = G.log_p_stay[st];
+    const float log_p_step_4 = G.log_p_step_4[st];
+    const unsigned n_km = a.n_train_kmers;
+
+    // the (sequence, event, chunk) items in the reference's order; every thread walks the same two cursors
+    struct Cursor { unsigned sq, i, base; };
+    auto skip = [&](Cursor& c) { while (c.sq < G.seq_end && (a.seqs[c.sq].strand != st || a.seqs[c.sq].n_events < 2)) ++c.sq; };
+    auto valid = [&](const Cursor& c) { return c.sq < G.seq_end; };
+    auto advance = [&](Cursor& c) {
+        c.base += ST_CHUNK;
+        if (c.base >= n_km)
+        {
+            c.base = 0;
+            if (++c.i + 1 >= a.seqs[c.sq].n_events) { c.i = 0; ++c.sq; skip(c); }
+        }
+    };
+    auto compute = [&](const Cursor& c, float (*term)[ST_CHUNK]) {
+        const int ct = t - 3 * 32;   // 0..415
+        const FbSeq& Q = a.seqs[c.sq];
         const unsigned n = Q.n_events;
         const float* E = a.scratch + Q.slab;
         const float* AL = a.scratch + Q.slab + 1 * (size_t)n * NC_N_STATES;
         const float* BE = a.scratch + Q.slab + 2 * (size_t)n * NC_N_STATES;
-        const float logz = a.log_pr_data[sq];
-        const float log_p_stay = G.log_p_stay[st];
-        const float log_p_step_4 = G.log_p_step_4[st];
-        for (unsigned i = 0; i + 1 < n; ++i)
+        const float logz = a.log_pr_data[c.sq];
+        const float* Ai = AL + (size_t)c.i * NC_N_STATES;
+        const float* Bi = BE + (size_t)c.i * NC_N_STATES;
+        const float* Bn = BE + (size_t)(c.i + 1) * NC_N_STATES;
+        const float* En = E + (size_t)(c.i + 1) * NC_N_STATES;
+        float t_denom = NC_NEG_INF, t_stay = NC_NEG_INF, t_skip = NC_NEG_INF;
+        if (c.base + ct < n_km)
         {
-            const float* Ai = AL + (size_t)i * NC_N_STATES;
-            const float* Bi = BE + (size_t)i * NC_N_STATES;
-            const float* Bn = BE + (size_t)(i + 1) * NC_N_STATES;
-            const float* En = E + (size_t)(i + 1) * NC_N_STATES;
-            for (unsigned base = 0; base < a.n_train_kmers; base += FB_THREADS)
-            {
-                float t_denom = NC_NEG_INF, t_stay = NC_NEG_INF, t_skip = NC_NEG_INF;
-                if (base + t < a.n_train_kmers)
-                {
-                    const unsigned j1 = a.train_kmers[base + t];
-                    const float al = Ai[j1];
-                    const float log_p_j1 = __fsub_rn(__fadd_rn(al, Bi[j1]), logz);
-                    // joint(i, j1, j2, lt) = alpha + lt + emission(j2, e_{i+1}) + beta(i+1, j2) - logZ   (:457-469)
-                    float jj = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_stay), En[j1]), Bn[j1]), logz);
-                    if (jj > log_p_j1) jj = log_p_j1;
-                    float s2 = flogsum(NC_NEG_INF, jj, tbl);
-                    const unsigned nb = (j1 & 1023u) << 2;
+            const unsigned j1 = a.train_kmers[c.base + ct];
+            const float al = Ai[j1];
+            const float log_p_j1 = __fsub_rn(__fadd_rn(al, Bi[j1]), logz);
+            // joint(i, j1, j2, lt) = alpha + lt + emission(j2, e_{i+1}) + beta(i+1, j2) - logZ   (:457-469)
+            float jj = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_stay), En[j1]), Bn[j1]), logz);
+            if (jj > log_p_j1) jj = log_p_j1;
+            float s2 = flogsum(NC_NEG_INF, jj, tbl);
+            const unsigned nb = (j1 & 1023u) << 2;   // the four one-step successors are one aligned float4
+            const float4 e4 = *reinterpret_cast< const float4* >(En + nb);
+            const float4 b4 = *reinterpret_cast< const float4* >(Bn + nb);
+            const float ev[4] = { e4.x, e4.y, e4.z, e4.w }, bv[4] = { b4.x, b4.y, b4.z, b4.w };
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                    {
-                        const float jv = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_step_4), En[nb + b]), Bn[nb + b]), logz);
-                        s2 = flogsum(s2, jv, tbl);
-                    }
-                    if (s2 > log_p_j1) s2 = log_p_j1;
-                    const float p2 = __fsub_rn(nc_expf(log_p_j1), nc_expf(s2));
-                    t_denom = log_p_j1;
-                    t_stay = jj;
-                    t_skip = nc_logf(p2);
-                }
-                term[0][t] = t_denom;
-                term[1][t] = t_stay;
-                term[2][t] = t_skip;
-                __syncthreads();
-                if (warp < 3)
-                {
-                    // NaN terms (log of a negative difference cannot occur: d01 <= post) are folded like the reference would
-                    const float* Tw = term[warp];
-                    const float acc = fold_logsum_in_order(accs[warp], FB_THREADS, [&](int k) { return Tw[k]; }, ss.lst[warp], tbl, lane);
-                    if (lane == 0) accs[warp] = acc;
-                }
-                __syncthreads();
+            for (int b = 0; b < 4; ++b)
+            {
+                const float jv = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_step_4), ev[b]), bv[b]), logz);
+                s2 = flogsum(s2, jv, tbl);
             }
+            if (s2 > log_p_j1) s2 = log_p_j1;
+            const float p2 = __fsub_rn(nc_expf(log_p_j1), nc_expf(s2));
+            t_denom = log_p_j1;
+            t_stay = jj;
+            t_skip = nc_logf(p2);
         }
+        term[0][ct] = t_denom;
+        term[1][ct] = t_stay;
+        term[2][ct] = t_skip;
+    };
+
+    __syncthreads();   // tbl
+    Cursor cc = { G.seq_begin, 0, 0 };
+    skip(cc);
+    if (valid(cc) && warp >= 3) compute(cc, ss.term[0]);
+    __syncthreads();
+    Cursor fc = cc;
+    advance(cc);
+    int buf = 0;
+    float acc = NC_NEG_INF;   // warps 0..2: denom, stay, skip
+    while (valid(fc))
+    {
+        if (warp >= 3)
+        {
+            if (valid(cc)) compute(cc, ss.term[buf ^ 1]);
+        }
+        else
+        {
+            // NaN terms (log of a negative difference cannot occur: d01 <= post) are folded like the reference would
+            const float* Tw = ss.term[buf][warp];
+            acc = fold_logsum_in_order(acc, ST_CHUNK, [&](int k) { return Tw[k]; }, ss.lst[warp], tbl, lane);
+        }
+        __syncthreads();
+        fc = cc;
+        advance(cc);
+        buf ^= 1;
     }
-    if (t < 3) a.st_stats[(grp * 2 + st) * 3 + t] = accs[t];   // denom, stay, skip
+    if (warp < 3 && lane == 0) a.st_stats[(grp * 2 + st) * 3 + warp] = acc;   // denom, stay, skip
 }
 
 } // namespace nc
