@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="0 = 2 per host thread")
+    ap.add_argument("--mix", action="store_true",
+                    help="read-length mixture of BASELINE.json configs[4] (90 %% ~5k, 9 %% 20-50k, 1 %% 100-150k events) "
+                         "instead of --events per read; not the default line")
     ap.add_argument("--vit-mode", default="auto", choices=["auto", "backpointer"],
                     help="auto = alpha-column kernel where the columns fit the pool; backpointer = long-read kernel only")
     return ap.parse_args()
@@ -196,8 +199,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     table = models.builtin_model(MODEL)["table"]
-    batch = synth.make_batch_uniform(args.seed + rank, table, args.reads, args.events)
-    total = args.reads * args.events
+    if args.mix:
+        lengths = synth.mixture_lengths(args.seed + rank, args.reads)
+        batch = synth.make_batch_uniform(args.seed + rank, table, args.reads, 0, lengths=lengths)
+        total = int(lengths.sum())
+    else:
+        batch = synth.make_batch_uniform(args.seed + rank, table, args.reads, args.events)
+        total = args.reads * args.events
 
     ctx = api.Context(local_rank)
     mid = ctx.register_model(table, 0)
@@ -296,7 +304,11 @@ def main():
             "metric": "viterbi_events_per_sec", "value": value, "unit": "events/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.reads} reads x {args.events} events per GPU, R7.3 template, "
+            "config": {"workload": (f"{args.reads} reads per GPU, length mixture 90 % ~5k / 9 % 20-50k / 1 % 100-150k events "
+                                    f"({total} events, longest {int(np.diff(batch['ev_off'].astype(np.int64)).max())}), R7.3 template, "
+                                    "fixed identity scaling, default transitions, Viterbi + traceback (configs[4] shape)")
+                       if args.mix else
+                                   f"{args.reads} reads x {args.events} events per GPU, R7.3 template, "
                                    "fixed identity scaling, default transitions, Viterbi + traceback (configs[1])",
                        "model": MODEL, "reads_per_gpu": args.reads, "events_per_read": args.events,
                        "l2": "inputs larger than L2: 12 B/event of events (1.2 GB per 1e8 events) and 16 KiB/event of alpha columns (164 MB per 10k-event read) stream through HBM, nothing is reused across steps",
@@ -324,7 +336,7 @@ def main():
             line["e2e"] = {"value": world * total * args.steps / e2e[0], "unit": "events/s",
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
                            "timing": "wall clock around nc_viterbi_packed(NC_MEM_HOST), pinned buffers"}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.mix:   # (a 150k-event read needs 4.9 GB per CPU thread)
             line["cpu_baseline"], _ = cpu_baseline(table, batch, args.events, args.cpu_sample_reads)
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -81,12 +81,28 @@ def random_params(rng, n):
     return p
 
 
-def make_batch_uniform(seed, table, n_reads, n_events, p_stay=0.1, p_skip=0.3):
-    """Vectorised generator for n_reads reads of exactly n_events events, identity scaling (bench
-    workloads: 10k x 10k).  One long stay/step/skip walk over a random base stream is cut into
-    reads; `start` restarts at 0 in every read."""
+def mixture_lengths(seed, n_reads):
+    """Read lengths of BASELINE.json configs[4]: 90 % LogNormal(median 5000, sigma 0.5)
+    clipped to [500, 20000), 9 % uniform 20k-50k, 1 % uniform 100k-150k events."""
     rng = np.random.default_rng(seed)
-    total = n_reads * n_events
+    u = rng.random(n_reads)
+    short = np.clip(rng.lognormal(np.log(5000.0), 0.5, n_reads), 500, 19999)
+    mid = rng.uniform(20000, 50000, n_reads)
+    lng = rng.uniform(100000, 150000, n_reads)
+    return np.where(u < 0.90, short, np.where(u < 0.99, mid, lng)).astype(np.int64)
+
+
+def make_batch_uniform(seed, table, n_reads, n_events, p_stay=0.1, p_skip=0.3, lengths=None):
+    """Vectorised generator for n_reads reads of exactly n_events events (or of the given lengths), identity
+    scaling (bench workloads: 10k x 10k, the length mixture).  One long stay/step/skip walk over a random base
+    stream is cut into reads; `start` restarts at 0 in every read."""
+    rng = np.random.default_rng(seed)
+    if lengths is not None:
+        lengths = np.asarray(lengths, np.int64)
+        n_reads = lengths.size
+        total = int(lengths.sum())
+    else:
+        total = n_reads * n_events
     u = rng.random(total, dtype=np.float32)
     move = np.where(u < p_stay, 0, np.where(u < 1.0 - p_skip, 1, 2)).astype(np.int64)
     del u
@@ -106,6 +122,13 @@ def make_batch_uniform(seed, table, n_reads, n_events, p_stay=0.1, p_skip=0.3):
     mean = (mu + sigma * rng.standard_normal(total, dtype=np.float32)).astype(np.float32)
     stdv = np.clip(rng.wald(eta, lam), 1e-3, 4.0).astype(np.float32)
     del eta, lam, t
+    if lengths is not None:
+        length = np.maximum(0.002, rng.exponential(0.02, total))
+        off = np.zeros(n_reads + 1, np.uint64)
+        off[1:] = np.cumsum(lengths)
+        run = np.cumsum(length) - length                      # start of each event on one global clock
+        first = np.repeat(run[off[:-1].astype(np.int64)], lengths)
+        return {"ev_off": off, "mean": mean, "stdv": stdv, "start": (run - first).astype(np.float32), "truth": states}
     length = np.maximum(0.002, rng.exponential(0.02, total)).reshape(n_reads, n_events)
     start = np.cumsum(length, axis=1) - length
     off = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(n_events))

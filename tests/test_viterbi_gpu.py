@@ -117,6 +117,26 @@ def test_long_read_traceback_blocks(ctx, port, models):
     _check_batch(ctx, port, table, mid, batch, None, None)
 
 
+_LONG_ORACLE = {}
+
+
+def test_read_of_100k_events(ctx, port, models, vit_mode):
+    """BASELINE.json configs[4] names reads of 100k+ events: one 102,400-event read next to a short one, bit-identical
+    to the oracle through either kernel (the reference's matrix for this read is 3.3 GB; here 1.6 GB of alpha columns
+    or 400 MB of backpointers)."""
+    table = models[R73T]["table"]
+    mid = ctx.register_model(table, 0)
+    batch = synth.make_batch_uniform(77, table, 0, 0, lengths=[102400, 900])
+    out = ctx.viterbi(batch["ev_off"], batch["mean"], batch["stdv"], batch["start"], mid)
+    if "exp" not in _LONG_ORACLE:   # ~30 s of CPU: computed once for both kernel modes
+        _LONG_ORACLE["exp"] = port.viterbi_batch(table, batch["ev_off"], batch["mean"], batch["stdv"], batch["start"],
+                                                 api._pm_array(None, 2), api._st_array(None, 2), n_threads=2)
+    exp = _LONG_ORACLE["exp"]
+    assert np.array_equal(_bits(out["path_logprob"]), _bits(exp["path_prob"]))
+    assert np.array_equal(out["states"].astype(np.uint32), exp["states"])
+    assert np.array_equal(out["moves"].astype(np.int32), exp["moves"])
+
+
 def test_per_job_pointer_api_and_base_seq(ctx, port, models):
     table = models[R73C2]["table"]
     mid = ctx.register_model(table, 1)
