@@ -58,6 +58,8 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
     if ((e = cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(stats)", e);
     if ((e = cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset(stats)", e);
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     unsigned hc = std::thread::hardware_concurrency();
     ctx->host_threads = hc ? std::min(hc, 32u) : 4u;
     *out = ctx;
@@ -80,6 +82,8 @@ void nc_ctx_destroy(nc_ctx* ctx)
     if (ctx->d_train_kmers) cudaFree(ctx->d_train_kmers);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -212,50 +216,75 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         }
     }
     // ---- which kernel decodes which job.  The alpha-column kernel is the fast path; it needs 16 KiB of scratch per
-    // event of every job in flight and two slabs per forward CTA (the traceback of one job overlaps the forward pass
-    // of the next); the backpointer kernel needs 4 KiB per event and one slab per CTA.  Jobs whose alpha columns fit
-    // a slab take the fast path, longer ones the backpointer kernel.  A call that wants no states (candidate
-    // ranking by path probability) needs no scratch at all.
+    // event, held in one private ring per forward CTA (two consecutive jobs that fit the ring together overlap forward
+    // pass and traceback; one job may use the whole ring).  The backpointer kernel needs 4 KiB per event and one slab
+    // per CTA.  Jobs whose alpha columns fit a ring take the fast path, longer ones the backpointer kernel; when both
+    // classes exist the two kernels run concurrently on disjoint sets of SMs (every CTA of either kernel fills an SM)
+    // and disjoint parts of the pool.  A call that wants no states (candidate ranking by path probability) needs no
+    // scratch at all.
     const bool want_path = states != nullptr || moves != nullptr;
     const size_t n_sms = (size_t)ctx->prop.multiProcessorCount;
     const size_t a_col = (size_t)NC_N_STATES * sizeof(float), b_col = (size_t)NC_N_STATES;
     // traceback service CTAs of the alpha kernel: one per ~36 forward CTAs (16 jobs in flight each)
     auto tb_ctas_for = [&](size_t fwd) { return want_path ? std::min< size_t >(4, (fwd + 35) / 36) : (size_t)0; };
-    size_t fwd_wanted = std::min< size_t >(n_jobs, n_sms);
-    while (fwd_wanted > 1 && fwd_wanted + tb_ctas_for(fwd_wanted) > n_sms) --fwd_wanted;
-    uint32_t alpha_max_len = 0xffffffffu;
-    if (want_path)
-        alpha_max_len = (uint32_t)std::min< size_t >((ctx->bp_bytes / (2 * fwd_wanted)) / a_col, 0xffffffffu);
-    if (ctx->vit_mode == NC_VIT_BACKPOINTER) alpha_max_len = 0;   // forced backpointer form (tests, A/B measurements)
+    auto fwd_ctas_in = [&](size_t ctas, size_t n_alpha_jobs) {   // forward CTAs when `ctas` SMs serve n_alpha_jobs jobs
+        size_t fwd = std::min< size_t >(n_alpha_jobs, ctas);
+        while (fwd > 1 && fwd + tb_ctas_for(fwd) > ctas) --fwd;
+        return fwd;
+    };
     std::vector< unsigned > order(n_jobs);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return jobs[a].n_events > jobs[b].n_events; });
     // order = [long jobs (backpointer form) | the rest (alpha form)], each longest first
+    uint32_t alpha_max_len = 0xffffffffu;
+    if (want_path) alpha_max_len = (uint32_t)std::min< size_t >((ctx->bp_bytes / fwd_ctas_in(n_sms, n_jobs)) / a_col, 0xffffffffu);
+    if (ctx->vit_mode == NC_VIT_BACKPOINTER) alpha_max_len = 0;   // forced backpointer form (tests, A/B measurements)
     uint32_t n_long = 0;
     while (n_long < n_jobs && jobs[order[n_long]].n_events > alpha_max_len) ++n_long;
-    const uint32_t n_short = n_jobs - n_long;
     unsigned grid_b = 0, fwd_a = 0, tb_a = 0;
-    size_t slab_b = 0, slab_a = 0;
-    if (n_long)
+    size_t slab_b = 0, slab_a = 0, pool_b = 0;
+    for (;;)
     {
-        slab_b = (size_t)max_len * b_col;
-        const size_t fit = ctx->bp_bytes / slab_b;
-        if (fit == 0)
-            NC_FAIL(ctx, NC_ERR_NOMEM, "nc_viterbi_packed: a %u-event job needs %zu backpointer bytes, pool has %zu",
-                    max_len, slab_b, ctx->bp_bytes);
-        grid_b = (unsigned)std::min< size_t >(std::min< size_t >(n_long, n_sms), fit);
-    }
-    if (n_short)
-    {
-        size_t fwd = std::min< size_t >(n_short, fwd_wanted);
-        if (want_path)
+        const uint32_t n_short = n_jobs - n_long;
+        grid_b = fwd_a = tb_a = 0;
+        slab_b = slab_a = pool_b = 0;
+        size_t sms_b = 0;
+        if (n_long)
         {
-            slab_a = (size_t)jobs[order[n_long]].n_events * a_col;
-            fwd = std::min< size_t >(fwd, ctx->bp_bytes / (2 * slab_a));
+            slab_b = (size_t)max_len * b_col;
+            const size_t fit = ctx->bp_bytes / slab_b;
+            if (fit == 0)
+                NC_FAIL(ctx, NC_ERR_NOMEM, "nc_viterbi_packed: a %u-event job needs %zu backpointer bytes, pool has %zu",
+                        max_len, slab_b, ctx->bp_bytes);
+            sms_b = std::min< size_t >(std::min< size_t >(n_long, n_sms), fit);
+            if (n_short)
+            {
+                // share the SMs by estimated time: the backpointer form costs ~1.85x per event
+                double ev_long = 0, ev_short = 0;
+                for (uint32_t k = 0; k < n_jobs; ++k) (k < n_long ? ev_long : ev_short) += jobs[order[k]].n_events;
+                const double share = 1.85 * ev_long / (1.85 * ev_long + ev_short);
+                size_t want = (size_t)(share * (double)n_sms + 0.5);
+                want = std::max< size_t >(1, std::min< size_t >(want, n_sms > 2 ? n_sms - 2 : 1));
+                sms_b = std::min(sms_b, want);
+            }
+            grid_b = (unsigned)sms_b;
+            pool_b = (size_t)grid_b * slab_b;
         }
-        fwd_a = (unsigned)fwd;
-        tb_a = (unsigned)tb_ctas_for(fwd);
+        if (n_short)
+        {
+            const size_t fwd = fwd_ctas_in(n_sms - sms_b, n_short);
+            fwd_a = (unsigned)fwd;
+            tb_a = (unsigned)tb_ctas_for(fwd);
+            if (want_path)
+            {
+                slab_a = ((ctx->bp_bytes - pool_b) / fwd) & ~(a_col - 1);
+                // the longest alpha job must fit this (smaller) ring: otherwise it joins the backpointer class
+                if ((size_t)jobs[order[n_long]].n_events * a_col > slab_a) { ++n_long; continue; }
+            }
+        }
+        break;
     }
+    const uint32_t n_short = n_jobs - n_long;
 
     int rc;
     if ((rc = dev_reserve(ctx, ctx->jobs, n_jobs * sizeof(nc::DevJob))) != NC_OK) return rc;
@@ -327,8 +356,12 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     ctx->last_launches = 0;
     if (n_long)
     {
-        nc::viterbi_kernel<<< grid_b, nc::VIT_THREADS, nc::viterbi_smem_bytes(), s >>>(a);
+        // on the second stream, so it runs next to the alpha kernel (grid_b + fwd_a + tb_a <= number of SMs)
+        cudaStream_t sb = n_short ? ctx->stream2 : s;
+        if (n_short) NC_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev0, 0));
+        nc::viterbi_kernel<<< grid_b, nc::VIT_THREADS, nc::viterbi_smem_bytes(), sb >>>(a);
         NC_CUDA(ctx, cudaGetLastError());
+        if (n_short) NC_CUDA(ctx, cudaEventRecord(ctx->ev2, sb));
         ++ctx->last_launches;
     }
     if (n_short)
@@ -337,12 +370,13 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         b.order = a.order + n_long;
         b.n_jobs = n_short;
         b.next_job = a.next_job + 1;
+        b.bp_pool = a.bp_pool + pool_b;
         b.slab_bytes = slab_a;
         b.n_fwd = fwd_a;
         b.n_tb = tb_a;
         if (want_path)
         {
-            // tickets | tail, head | per-slab release counters, zeroed
+            // tickets | tail, head | per-parity release counters of every forward CTA, zeroed
             const size_t tk_bytes = (size_t)n_short * sizeof(nc::TbTicket);
             const size_t ctl_bytes = (2 + 2 * (size_t)fwd_a) * sizeof(unsigned);
             if ((rc = dev_reserve(ctx, ctx->tb, tk_bytes + ctl_bytes)) != NC_OK) return rc;
@@ -355,6 +389,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         nc::viterbi_alpha_kernel<<< fwd_a + tb_a, nc::VIT_THREADS, nc::viterbi_alpha_smem_bytes(), s >>>(b);
         NC_CUDA(ctx, cudaGetLastError());
         ++ctx->last_launches;
+        if (n_long) NC_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev2, 0));
     }
     NC_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
 

@@ -21,6 +21,8 @@ struct nc_ctx
 {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // backpointer-kernel launches that run next to the alpha kernel
+    cudaEvent_t ev2 = nullptr;
     cudaDeviceProp prop;
     std::vector< nc::HostModel > models;
     float* d_models = nullptr;

@@ -13,9 +13,11 @@ enum { VIT_THREADS = 512 };
 struct TbTicket
 {
     unsigned job;          // index into jobs
-    unsigned slab;         // slab holding the job's alpha columns
+    unsigned slab;         // release counter of the job: 2 * forward CTA + (job parity); slab >> 1 = the CTA's ring
     unsigned final_state;  // arg max of the last column
     unsigned ready;        // written last (release); polled with acquire
+    unsigned col0;         // first column of the job inside the ring
+    unsigned pad[3];
 };
 
 struct VitArgs
@@ -29,8 +31,8 @@ struct VitArgs
     const float* stdv;
     const float* start;
     const float* log_stdv;
-    unsigned char* bp_pool;     // gridDim.x slabs of slab_bytes: backpointers (viterbi_kernel, 4096 B/event) or
-                                // alpha columns (viterbi_alpha_kernel, 16384 B/event)
+    unsigned char* bp_pool;     // viterbi_kernel: gridDim.x slabs of slab_bytes of backpointers (4096 B/event);
+                                // viterbi_alpha_kernel: n_fwd rings of slab_bytes of alpha columns (16384 B/event)
     size_t slab_bytes;
     float* path_logprob;        // n_jobs
     unsigned short* states;     // packed like the events, may be null
@@ -38,7 +40,7 @@ struct VitArgs
     float log_2pi;              // (float)log(2*pi)  (Pore_Model.hpp:28)
     float log_n_states;         // logf(4096.f)      (Viterbi.hpp:51)
     // alpha-column kernel only: CTAs [0, n_tb) are traceback service warps fed through `tickets`, the other n_fwd
-    // CTAs run forward passes (two slabs each: 2*f, 2*f+1 for forward CTA f)
+    // CTAs run forward passes (one ring each; release counters 2*f, 2*f+1 for the jobs of even / odd parity)
     unsigned n_fwd, n_tb;
     TbTicket* tickets;          // n_jobs entries, zeroed before the launch
     unsigned* tb_tail;          // tickets published

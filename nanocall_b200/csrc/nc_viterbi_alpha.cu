@@ -302,6 +302,10 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
     const unsigned T = (unsigned)t >> 1, half = (unsigned)t & 1u;
     const bool keep = a.states != nullptr;   // path probability only: nothing to trace back, nothing stored
     unsigned jobs_done = 0;
+    // this CTA's private ring of alpha columns (slab_bytes each) and the region of its previous job
+    float* const ring = reinterpret_cast< float* >(a.bp_pool + (size_t)(blockIdx.x - a.n_tb) * a.slab_bytes);
+    const unsigned ring_cols = (unsigned)(a.slab_bytes / (NC_N_STATES * sizeof(float)));
+    unsigned prev_start = 0, prev_cols = 0;
     const float log_2pi = a.log_2pi;
     const float hl2pi = __fmul_rn(0.5f, a.log_2pi);
     const unsigned bar = smem_u32(&sm.col_bar);
@@ -319,21 +323,32 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
         const DevJob& J = a.jobs[job_idx];
         const unsigned n = J.n_events;
         const unsigned long long off = J.ev_off;
-        // this job's slab: the CTA owns two and alternates; the previous user of the slab (job k-2 of this CTA) must
-        // have been traced back, i.e. the slab released (k >> 1) times so far
+        // Placement of this job's n alpha columns in the ring: right after the previous job's, or at the start of
+        // the ring when they would not fit behind it (a job never wraps).  At most two jobs of a CTA are live: job
+        // k-2 must have been traced back before job k starts (release counter of parity k & 1), and job k-1 too if
+        // the new region overlaps its columns.  Two consecutive jobs that fit the ring together therefore overlap
+        // forward pass and traceback, and a single job may use the whole ring.
         const unsigned slab_id = 2u * (blockIdx.x - a.n_tb) + (jobs_done & 1u);
-        float* const acol = reinterpret_cast< float* >(a.bp_pool + (size_t)slab_id * a.slab_bytes);
-        if (keep && jobs_done >= 2)
+        unsigned col0 = prev_start + prev_cols;
+        if (col0 + n > ring_cols) col0 = 0;
+        const bool hits_prev = jobs_done >= 1 && col0 < prev_start + prev_cols && prev_start < col0 + n;
+        float* const acol = ring + (size_t)col0 * NC_N_STATES;
+        if (keep && jobs_done >= 1)
         {
             if (t == 0)
             {
                 const long long c0 = clock64();
                 unsigned ns = 64;
-                while (ld_acquire_u32(a.slab_free + slab_id) < (jobs_done >> 1)) { __nanosleep(ns); if (ns < 4096) ns *= 2; }
+                if (jobs_done >= 2)
+                    while (ld_acquire_u32(a.slab_free + slab_id) < (jobs_done >> 1)) { __nanosleep(ns); if (ns < 4096) ns *= 2; }
+                if (hits_prev)
+                    while (ld_acquire_u32(a.slab_free + (slab_id ^ 1u)) < ((jobs_done - 1) >> 1) + 1u) { __nanosleep(ns); if (ns < 4096) ns *= 2; }
                 if (a.stats) atomicAdd(a.stats + 1, (unsigned long long)(clock64() - c0));
             }
             __syncthreads();
         }
+        prev_start = col0;
+        prev_cols = n;
         const long long fwd_c0 = clock64();
 
         // ---------------- prologue: scaled model constants (as state pairs) and transition weights
@@ -540,8 +555,8 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
         }
 
         // ---------------- hand the traceback to a service warp (other CTAs of this grid) and go on with the next job.
-        // The alpha columns of this job stay in the slab until the service warp releases it; the CTA alternates
-        // between its two slabs, so the forward pass of job k+1 overlaps the traceback of job k.
+        // The alpha columns of this job stay in the ring until the service warp releases them (counter slab_id), so
+        // the forward pass of job k+1 overlaps the traceback of job k.
         if (keep)
         {
             __threadfence();        // every thread: its alpha stores are visible device-wide before the ticket is
@@ -552,6 +567,7 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
                 TbTicket& tk = a.tickets[slot];
                 tk.job = job_idx;
                 tk.slab = slab_id;
+                tk.col0 = col0;
                 tk.final_state = (unsigned)sm.final_state;
                 __threadfence();
                 st_release_u32(&tk.ready, 1u);
@@ -588,10 +604,11 @@ __device__ void traceback_service(const VitArgs& a)
         const long long w1 = clock64();
         unsigned passes = 0, steps = 0;
         const unsigned job_idx = __ldcg(&tk.job), slab_id = __ldcg(&tk.slab), final_state = __ldcg(&tk.final_state);
+        const unsigned col0 = __ldcg(&tk.col0);
         const DevJob& J = a.jobs[job_idx];
         const unsigned n = J.n_events;
         const float* lut = J.lut;
-        const float* acol = reinterpret_cast< const float* >(a.bp_pool + (size_t)slab_id * a.slab_bytes);
+        const float* acol = reinterpret_cast< const float* >(a.bp_pool + (size_t)(slab_id >> 1) * a.slab_bytes) + (size_t)col0 * NC_N_STATES;
         unsigned short* out_s = a.states + J.ev_off;
         const unsigned T = n - 1;  // transitions: column c in 1..T is entered from column c-1
         if (T == 0)
