@@ -225,8 +225,9 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     const bool want_path = states != nullptr || moves != nullptr;
     const size_t n_sms = (size_t)ctx->prop.multiProcessorCount;
     const size_t a_col = (size_t)NC_N_STATES * sizeof(float), b_col = (size_t)NC_N_STATES;
-    // traceback service CTAs of the alpha kernel: one per ~36 forward CTAs (16 jobs in flight each)
-    auto tb_ctas_for = [&](size_t fwd) { return want_path ? std::min< size_t >(4, (fwd + 35) / 36) : (size_t)0; };
+    // traceback service CTAs of the alpha kernel: one per ~48 forward CTAs (16 jobs in flight each; measured busy
+    // 22 % of the time at one per 36)
+    auto tb_ctas_for = [&](size_t fwd) { return want_path ? std::max< size_t >(1, std::min< size_t >(4, (fwd + 24) / 48)) : (size_t)0; };
     auto fwd_ctas_in = [&](size_t ctas, size_t n_alpha_jobs) {   // forward CTAs when `ctas` SMs serve n_alpha_jobs jobs
         size_t fwd = std::min< size_t >(n_alpha_jobs, ctas);
         while (fwd > 1 && fwd + tb_ctas_for(fwd) > ctas) --fwd;

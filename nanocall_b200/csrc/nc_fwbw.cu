@@ -399,14 +399,26 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
                         else if (sInO) mpos = (oBef ? 0 : 16) + (j & 3);
                         // otherwise: number of blocks entirely below j
                         const int pos = (mpos >= 0) ? -1 : ((j > tb ? 1 : 0) + ((!oIn && j > ob[f]) ? 1 : 0));
-                        float acc = NC_NEG_INF;
-                        acc = flogsum(acc, pos == 0 ? vS : NC_NEG_INF, tbl);
-#pragma unroll
-                        for (int q = 0; q < 20; ++q)
+                        // p7_FLogsum(-inf, x) == x: the first fold is a select
+                        float acc = (pos == 0) ? vS : NC_NEG_INF;
+                        if (mpos < 0)
                         {
-                            if (q == 4) acc = flogsum(acc, (oBef && pos == 1) ? vS : NC_NEG_INF, tbl);
-                            if (q == 16) acc = flogsum(acc, (!oBef && pos == 1) ? vS : NC_NEG_INF, tbl);
-                            acc = flogsum(acc, (q == mpos) ? vS : L[q], tbl);
+                            // common case: j is not one of its own block successors, the list is used as it is
+#pragma unroll
+                            for (int q = 0; q < 20; ++q)
+                            {
+                                if (q == 4) acc = flogsum(acc, (oBef && pos == 1) ? vS : NC_NEG_INF, tbl);
+                                if (q == 16) acc = flogsum(acc, (!oBef && pos == 1) ? vS : NC_NEG_INF, tbl);
+                                acc = flogsum(acc, L[q], tbl);
+                            }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int q = 0; q < 20; ++q)
+                            {
+                                acc = flogsum(acc, (q == mpos) ? vS : L[q], tbl);   // (pos == -1: no fold between the blocks)
+                            }
                         }
                         acc = flogsum(acc, pos == 2 ? vS : NC_NEG_INF, tbl);
                         Bc[cphys(j)] = acc;
