@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -60,6 +61,14 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev3, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->d_landed, sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(landed)", e);
+    if ((e = cudaHostAlloc(&ctx->h_landed, nc_ctx::LANDED_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess)
+        return fail("cudaHostAlloc(landed)", e);
+    // streamed event upload (nc_viterbi_packed, host memory): thresholds, overridable for tests
+    if (const char* v = std::getenv("NC_STREAM_IN_MIN_EVENTS")) ctx->stream_in_min_events = std::strtoull(v, nullptr, 10);
+    if (const char* v = std::getenv("NC_STREAM_IN_CHUNK")) ctx->stream_in_chunk = std::max< uint64_t >(32, std::strtoull(v, nullptr, 10));
     unsigned hc = std::thread::hardware_concurrency();
     ctx->host_threads = hc ? std::min(hc, 32u) : 4u;
     *out = ctx;
@@ -84,6 +93,10 @@ void nc_ctx_destroy(nc_ctx* ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream3) { cudaStreamSynchronize(ctx->stream3); cudaStreamDestroy(ctx->stream3); }
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    if (ctx->d_landed) cudaFree(ctx->d_landed);
+    if (ctx->h_landed) cudaFreeHost(ctx->h_landed);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -315,6 +328,9 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     a.stats = ctx->d_stats;
 
     const uint64_t base = ev_off[0];
+    bool stream_in = false;
+    a.landed = nullptr;
+    a.ev_total = total;
     if (mem == NC_MEM_HOST)
     {
         const float* lsp = log_stdv ? log_stdv + base : nullptr;  // NULL: the kernel derives it (nc_logf)
@@ -322,10 +338,22 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         if ((rc = dev_reserve(ctx, ctx->stdv, total * sizeof(float))) != NC_OK) return rc;
         if ((rc = dev_reserve(ctx, ctx->start, total * sizeof(float))) != NC_OK) return rc;
         if (lsp && (rc = dev_reserve(ctx, ctx->lstd, total * sizeof(float))) != NC_OK) return rc;
-        NC_CUDA(ctx, cudaMemcpyAsync(ctx->mean.p, mean + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
-        NC_CUDA(ctx, cudaMemcpyAsync(ctx->stdv.p, stdv + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
-        NC_CUDA(ctx, cudaMemcpyAsync(ctx->start.p, start + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
-        if (lsp) NC_CUDA(ctx, cudaMemcpyAsync(ctx->lstd.p, lsp, total * sizeof(float), cudaMemcpyHostToDevice, s));
+        // Big batches: the kernels start at once and the event arrays follow on a third stream in chunks; a job
+        // waits (wait_events_landed) until the copy engine has delivered its events.  Small ones: plain copies.
+        stream_in = total >= ctx->stream_in_min_events;
+        if (stream_in)
+        {
+            NC_CUDA(ctx, cudaMemsetAsync(ctx->d_landed, 0, sizeof(unsigned long long), s));
+            NC_CUDA(ctx, cudaEventRecord(ctx->ev3, s));
+        }
+        else
+        {
+            NC_CUDA(ctx, cudaMemcpyAsync(ctx->mean.p, mean + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
+            NC_CUDA(ctx, cudaMemcpyAsync(ctx->stdv.p, stdv + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
+            NC_CUDA(ctx, cudaMemcpyAsync(ctx->start.p, start + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
+            if (lsp) NC_CUDA(ctx, cudaMemcpyAsync(ctx->lstd.p, lsp, total * sizeof(float), cudaMemcpyHostToDevice, s));
+        }
+        if (stream_in) a.landed = ctx->d_landed;
         a.mean = (const float*)ctx->mean.p;
         a.stdv = (const float*)ctx->stdv.p;
         a.start = (const float*)ctx->start.p;
@@ -392,6 +420,26 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         ++ctx->last_launches;
         if (n_long) NC_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev2, 0));
     }
+    if (stream_in)
+    {
+        // the kernels are queued; now feed them.  Chunks are multiples of 32 events (whole 128-byte lines).
+        cudaStream_t sc = ctx->stream3;
+        NC_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev3, 0));
+        const float* lsp = log_stdv ? log_stdv + base : nullptr;
+        uint64_t chunk = std::max< uint64_t >(ctx->stream_in_chunk, (total + nc_ctx::LANDED_SLOTS - 1) / nc_ctx::LANDED_SLOTS);
+        chunk = (chunk + 31) & ~(uint64_t)31;
+        int slot = 0;
+        for (uint64_t c0 = 0; c0 < total; c0 += chunk, ++slot)
+        {
+            const uint64_t c1 = std::min(total, c0 + chunk), nb = (c1 - c0) * sizeof(float);
+            NC_CUDA(ctx, cudaMemcpyAsync((float*)ctx->mean.p + c0, mean + base + c0, nb, cudaMemcpyHostToDevice, sc));
+            NC_CUDA(ctx, cudaMemcpyAsync((float*)ctx->stdv.p + c0, stdv + base + c0, nb, cudaMemcpyHostToDevice, sc));
+            NC_CUDA(ctx, cudaMemcpyAsync((float*)ctx->start.p + c0, start + base + c0, nb, cudaMemcpyHostToDevice, sc));
+            if (lsp) NC_CUDA(ctx, cudaMemcpyAsync((float*)ctx->lstd.p + c0, lsp + c0, nb, cudaMemcpyHostToDevice, sc));
+            ctx->h_landed[slot] = c1;
+            NC_CUDA(ctx, cudaMemcpyAsync(ctx->d_landed, ctx->h_landed + slot, sizeof(unsigned long long), cudaMemcpyHostToDevice, sc));
+        }
+    }
     NC_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
 
     NC_CUDA(ctx, cudaMemcpyAsync(path_logprob, ctx->path.p, n_jobs * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -401,6 +449,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         if (moves) NC_CUDA(ctx, cudaMemcpyAsync(moves + base, ctx->moves.p, total, cudaMemcpyDeviceToHost, s));
     }
     NC_CUDA(ctx, cudaStreamSynchronize(s));
+    if (stream_in) NC_CUDA(ctx, cudaStreamSynchronize(ctx->stream3));
     NC_CUDA(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
     return NC_OK;
 }

@@ -23,6 +23,13 @@ struct nc_ctx
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // backpointer-kernel launches that run next to the alpha kernel
     cudaEvent_t ev2 = nullptr;
+    cudaStream_t stream3 = nullptr;   // streamed event upload of host-memory calls
+    cudaEvent_t ev3 = nullptr;
+    unsigned long long* d_landed = nullptr;
+    unsigned long long* h_landed = nullptr;   // pinned: the values the copy stream writes into d_landed
+    static constexpr int LANDED_SLOTS = 1024;
+    uint64_t stream_in_min_events = (uint64_t)8 << 20;   // calls with fewer events copy everything before the launch
+    uint64_t stream_in_chunk = (uint64_t)4 << 20;        // events per chunk of the streamed upload
     cudaDeviceProp prop;
     std::vector< nc::HostModel > models;
     float* d_models = nullptr;

@@ -31,6 +31,8 @@ struct VitArgs
     const float* stdv;
     const float* start;
     const float* log_stdv;
+    const unsigned long long* landed;  // null, or the number of events already copied to the device (streamed input)
+    unsigned long long ev_total;       // events in the call
     unsigned char* bp_pool;     // viterbi_kernel: gridDim.x slabs of slab_bytes of backpointers (4096 B/event);
                                 // viterbi_alpha_kernel: n_fwd rings of slab_bytes of alpha columns (16384 B/event)
     size_t slab_bytes;

@@ -52,15 +52,35 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Host-memory calls stream the event arrays to the device while the kernels already run (nc_viterbi_packed): `landed`
+// counts the events whose copy has completed, in multiples of 32 so that every 128-byte line a job touches is whole
+// before the job starts.  One thread polls; the caller synchronises the CTA afterwards.
+__device__ __forceinline__ void wait_events_landed(const VitArgs& a, unsigned long long off, unsigned n)
+{
+    unsigned long long need = (off + n + 31ull) & ~31ull;
+    if (need > a.ev_total) need = a.ev_total;
+    unsigned ns = 256;
+    for (;;)
+    {
+        unsigned long long have;
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(have) : "l"(a.landed) : "memory");
+        if (have >= need) break;
+        __nanosleep(ns);
+        if (ns < 8192) ns *= 2;
+    }
+    __threadfence();
+}
+
 __device__ __forceinline__ EvRegs ev_load(const VitArgs& a, unsigned long long off, unsigned i, unsigned n)
 {
     EvRegs r;
     if (i < n)
     {
-        r.mean = __ldg(a.mean + off + i);
-        r.stdv = __ldg(a.stdv + off + i);
-        r.start = __ldg(a.start + off + i);
-        r.lstd = a.log_stdv ? __ldg(a.log_stdv + off + i) : nc_logf(r.stdv == 0.0f ? 0.01f : r.stdv);
+        // read once, and possibly written by the copy engine during this launch: L2 only
+        r.mean = __ldcg(a.mean + off + i);
+        r.stdv = __ldcg(a.stdv + off + i);
+        r.start = __ldcg(a.start + off + i);
+        r.lstd = a.log_stdv ? __ldcg(a.log_stdv + off + i) : nc_logf(r.stdv == 0.0f ? 0.01f : r.stdv);
     }
     else { r.mean = 0.f; r.stdv = 1.f; r.start = 0.f; r.lstd = 0.f; }
     return r;

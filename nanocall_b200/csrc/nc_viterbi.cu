@@ -73,6 +73,11 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_kernel(const VitArgs a
         const DevJob& J = a.jobs[job_idx];
         const unsigned n = J.n_events;
         const unsigned long long off = J.ev_off;
+        if (a.landed)
+        {
+            if (t == 0) wait_events_landed(a, off, n);
+            __syncthreads();
+        }
 
         // ---------------- prologue: scaled model constants and transition weights into registers
         StateParamsH P[SPT];

@@ -323,6 +323,11 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
         const DevJob& J = a.jobs[job_idx];
         const unsigned n = J.n_events;
         const unsigned long long off = J.ev_off;
+        if (a.landed)
+        {
+            if (t == 0) wait_events_landed(a, off, n);
+            __syncthreads();
+        }
         // Placement of this job's n alpha columns in the ring: right after the previous job's, or at the start of
         // the ring when they would not fit behind it (a job never wraps).  At most two jobs of a CTA are live: job
         // k-2 must have been traced back before job k starts (release counter of parity k & 1), and job k-1 too if

@@ -218,6 +218,23 @@ def test_mixed_dispatch_small_pool(port, models, vit_mode):
         c.close()
 
 
+def test_streamed_event_upload(port, models, vit_mode, monkeypatch):
+    """Host-memory calls above a size threshold start the kernels first and stream the events behind them in chunks
+    (jobs wait for their events to land).  Forced here on a small batch with 4096-event chunks: same bits."""
+    monkeypatch.setenv("NC_STREAM_IN_MIN_EVENTS", "0")
+    monkeypatch.setenv("NC_STREAM_IN_CHUNK", "4096")
+    table = models[R73T]["table"]
+    c = api.Context(0, bp_pool_bytes=2 << 30)
+    try:
+        from nanocall_b200 import _lib as L
+        c.set_viterbi_mode(L.NC_VIT_BACKPOINTER if vit_mode == "backpointer" else L.NC_VIT_AUTO)
+        mid = c.register_model(table, 0)
+        batch = synth.make_batch(53, table, [5000, 33, 1200, 7000, 250, 4097, 640] * 3)
+        _check_batch(c, port, table, mid, batch, None, None)
+    finally:
+        c.close()
+
+
 def test_path_probability_only_needs_no_scratch(port, models, vit_mode):
     """states=NULL, moves=NULL (candidate ranking): no columns are stored, so even a tiny pool serves long jobs."""
     if vit_mode != "alpha":
