@@ -43,8 +43,11 @@ typedef enum { NC_MEM_HOST = 0, NC_MEM_DEVICE = 1 } nc_mem;
 
 typedef struct nc_ctx nc_ctx;
 
-/* One context per GPU (and per host dispatcher thread).  bp_pool_bytes = device bytes reserved for
- * Viterbi backpointers (4096 B per event of every job in flight); 0 = pick from free memory. */
+/* One context per GPU (and per host dispatcher thread).  bp_pool_bytes = device bytes reserved for the Viterbi
+ * scratch of the jobs in flight (alpha columns, 16 KiB per event, or backpointers, 4 KiB per event, for reads
+ * too long for a forward CTA's share of the pool); 0 = 3/5 of the free memory, at most 100 GB.
+ * Environment (read here, for tests): NC_STREAM_IN_MIN_EVENTS / NC_STREAM_IN_CHUNK = size from which
+ * host-memory calls stream their events behind the kernel launch, and the chunk size, in events. */
 int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out);
 void nc_ctx_destroy(nc_ctx* ctx);
 const char* nc_last_error(const nc_ctx* ctx); /* ctx may be NULL: error of a failed nc_ctx_create */
@@ -55,13 +58,13 @@ int nc_ctx_sync(nc_ctx* ctx);
 float nc_ctx_last_kernel_ms(nc_ctx* ctx);
 /* kernels launched by the most recent nc_viterbi_packed call (bench.py's gpu_launches) */
 int nc_ctx_last_launches(nc_ctx* ctx);
-/* Viterbi kernel choice: NC_VIT_AUTO = alpha-column kernel for every job whose columns fit a pool slab (16 KiB per
+/* Viterbi kernel choice: NC_VIT_AUTO = alpha-column kernel for every job whose columns fit a forward CTA's ring (16 KiB per
  * event), backpointer kernel (4 KiB per event) for longer jobs; NC_VIT_BACKPOINTER = backpointer kernel only.
  * Both produce the reference's bits; the switch exists for A/B measurements and tests. */
 typedef enum { NC_VIT_AUTO = 0, NC_VIT_BACKPOINTER = 2 } nc_vit_mode;
 int nc_ctx_set_viterbi_mode(nc_ctx* ctx, int mode);
 /* Device-side counters of the alpha-column kernel, summed over CTAs / traceback service warps since the last
- * reset, in SM clock cycles: [0] forward passes, [1] forward CTAs waiting for a free slab, [2] traceback busy,
+ * reset, in SM clock cycles: [0] forward passes, [1] forward CTAs waiting for ring space, [2] traceback busy,
  * [3] traceback waiting for work, then counts: [4] traceback passes, [5] traceback lane steps, [6] jobs traced. */
 int nc_ctx_viterbi_stats(nc_ctx* ctx, uint64_t* out8, int reset);
 /* number of SMs / name of the device, for reports */
