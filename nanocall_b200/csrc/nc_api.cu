@@ -429,15 +429,26 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         uint64_t chunk = std::max< uint64_t >(ctx->stream_in_chunk, (total + nc_ctx::LANDED_SLOTS - 1) / nc_ctx::LANDED_SLOTS);
         chunk = (chunk + 31) & ~(uint64_t)31;
         int slot = 0;
-        for (uint64_t c0 = 0; c0 < total; c0 += chunk, ++slot)
+        cudaError_t ce = cudaSuccess;
+        for (uint64_t c0 = 0; c0 < total && ce == cudaSuccess; c0 += chunk, ++slot)
         {
             const uint64_t c1 = std::min(total, c0 + chunk), nb = (c1 - c0) * sizeof(float);
-            NC_CUDA(ctx, cudaMemcpyAsync((float*)ctx->mean.p + c0, mean + base + c0, nb, cudaMemcpyHostToDevice, sc));
-            NC_CUDA(ctx, cudaMemcpyAsync((float*)ctx->stdv.p + c0, stdv + base + c0, nb, cudaMemcpyHostToDevice, sc));
-            NC_CUDA(ctx, cudaMemcpyAsync((float*)ctx->start.p + c0, start + base + c0, nb, cudaMemcpyHostToDevice, sc));
-            if (lsp) NC_CUDA(ctx, cudaMemcpyAsync((float*)ctx->lstd.p + c0, lsp + c0, nb, cudaMemcpyHostToDevice, sc));
+            ce = cudaMemcpyAsync((float*)ctx->mean.p + c0, mean + base + c0, nb, cudaMemcpyHostToDevice, sc);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync((float*)ctx->stdv.p + c0, stdv + base + c0, nb, cudaMemcpyHostToDevice, sc);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync((float*)ctx->start.p + c0, start + base + c0, nb, cudaMemcpyHostToDevice, sc);
+            if (ce == cudaSuccess && lsp) ce = cudaMemcpyAsync((float*)ctx->lstd.p + c0, lsp + c0, nb, cudaMemcpyHostToDevice, sc);
             ctx->h_landed[slot] = c1;
-            NC_CUDA(ctx, cudaMemcpyAsync(ctx->d_landed, ctx->h_landed + slot, sizeof(unsigned long long), cudaMemcpyHostToDevice, sc));
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(ctx->d_landed, ctx->h_landed + slot, sizeof(unsigned long long), cudaMemcpyHostToDevice, sc);
+        }
+        if (ce != cudaSuccess)
+        {
+            // never leave the kernels waiting for events that will not come: declare everything landed, drain, fail
+            ctx->h_landed[0] = total;
+            cudaMemcpyAsync(ctx->d_landed, ctx->h_landed, sizeof(unsigned long long), cudaMemcpyHostToDevice, sc);
+            cudaStreamSynchronize(sc);
+            cudaStreamSynchronize(s);
+            NC_FAIL(ctx, NC_ERR_CUDA, "nc_viterbi_packed: streamed event upload failed: %s", cudaGetErrorString(ce));
         }
     }
     NC_CUDA(ctx, cudaEventRecord(ctx->ev1, s));

@@ -20,16 +20,8 @@ R73 = ["r73.t.006.ont.model", "r73.c.p1.006.ont.model", "r73.c.p2.006.ont.model"
 
 
 def _make_reads(models, seed, n_reads, nt=600, nc=500, comp="r73.c.p1.006.ont.model"):
-    rng = np.random.default_rng(seed)
-    reads = []
-    for k in range(n_reads):
-        pm = tuple(synth.random_params(rng, 1)[0])
-        t = synth.make_read(rng, models[R73[0]]["table"], nt + 17 * k, pm)
-        c = synth.make_read(rng, models[comp if k % 2 == 0 else R73[2]]["table"], nc + 11 * k, pm)
-        # complement starts where the template ended (start is relative to the template start when scaled together)
-        c["start"] = (c["start"] + t["start"][-1] + np.float32(0.5)).astype(np.float32)
-        reads.append((f"read{k}", [t, c]))
-    return reads
+    import pipeline_reads
+    return pipeline_reads.make_reads(models, seed, n_reads, nt=nt, nc=nc, comp=comp)
 
 
 def _run_cli(tmp_path, reads, extra):
@@ -131,3 +123,60 @@ def test_events_tsv_input(tmp_path, port, models):
     assert text[0] == ">tsvread:one:0"
     seqs = "".join(text).split(">")
     assert seqs[1].replace("tsvread:one:0", "") == exp["calls"][0]["bases"]
+
+
+def _edit_distance(a, b):
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+def test_pipeline_parity_golden(tmp_path, models):
+    """north_star's acceptance numbers on a few hundred reads: the full pipeline (EM training rounds, candidate-model
+    selection, Viterbi with the trained parameters) through the CLI against results computed with the reference's own
+    code on the CPU (tools/make_pipeline_golden.py, committed under tests/golden/).  Bars: basecalls identical on
+    >= 99.9 % of reads (edit distance reported for the rest), trained scaling parameters within 1e-4 relative, same
+    number of EM rounds, same selected model.  The report goes to gpurun_out/ when that directory exists."""
+    import gzip
+    import json
+    path = os.path.join(ROOT, "tests", "golden", "pipeline_r73.json.gz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/pipeline_r73.json.gz not generated")
+    with gzip.open(path, "rt") as f:
+        gold = json.load(f)
+    reads = _make_reads(models, gold["seed"], gold["n_reads"], nt=gold["nt"], nc=gold["nc"])
+    fa, stderr, _ = _run_cli(str(tmp_path), reads, [])
+    sc = _parse_scaling(stderr)
+    n_same, worst_pm, diffs, n_sel_same, n_rounds_same, n_keys = 0, 0.0, [], 0, 0, 0
+    for (rid, _), g in zip(reads, gold["reads"]):
+        assert g["read"] == rid
+        same = True
+        for st in range(2):
+            got = fa.get(f"{rid}:batch:{st}", "")
+            if got != g["bases"][st]:
+                same = False
+                diffs.append(dict(read=rid, strand=st, edit_distance=_edit_distance(got, g["bases"][st]), length=len(g["bases"][st])))
+        n_same += same
+        for key, pm in g["pm"].items():
+            got = sc[(rid, 2, key)]
+            n_keys += 1
+            n_rounds_same += got["rounds"] == g["rounds"][key]
+            worst_pm = max(worst_pm, float(_rel(got["pm"], pm)))
+        sel = g["preferred"]
+        has = f"selected_model read [{rid}] strand [2]" in stderr
+        n_sel_same += (has == (sel is not None)) and (sel is None or f"selected_model read [{rid}] strand [2] model [{sel}]" in stderr)
+    n = len(reads)
+    report = dict(n_reads=n, oracle=gold["oracle"], reads_with_identical_basecalls=n_same, identical_fraction=n_same / n,
+                  differing=diffs, worst_relative_pm_param_difference=worst_pm, candidates=n_keys,
+                  candidates_with_same_round_count=n_rounds_same, reads_with_same_model_selection=n_sel_same)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "pipeline_parity_report.json"), "w") as f:
+            json.dump(report, f, indent=1)
+    assert n_same / n >= 0.999, report
+    assert worst_pm < 1e-4 + 2e-6, report          # the log prints 6 significant digits
+    assert n_rounds_same == n_keys and n_sel_same == n, report
