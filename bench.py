@@ -41,7 +41,7 @@ HBM_BYTES_PER_EVENT = 4112
 FP32_OPS_PER_EVENT = 245600
 RF_READS_PER_EVENT = 404 * 512  # operand reads per thread and column x threads (nc_viterbi_alpha.cu header)
 # dram__bytes_read.sum + dram__bytes_write.sum per event of viterbi_alpha_kernel, from the committed capture
-NCU_DRAM_BYTES_PER_EVENT = {"viterbi_alpha_kernel": 17022.0, "source": "profiles/r1_ncu_viterbi_alpha_v2_summary.md"}
+NCU_DRAM_BYTES_PER_EVENT = {"viterbi_alpha_kernel": 17022.0, "source": "profiles/r1_ncu_viterbi_alpha_final_summary.md"}
 MODEL = "r73.t.006.ont.model"
 
 
