@@ -45,7 +45,7 @@ typedef struct nc_ctx nc_ctx;
 
 /* One context per GPU (and per host dispatcher thread).  bp_pool_bytes = device bytes reserved for the Viterbi
  * scratch of the jobs in flight (alpha columns, 16 KiB per event, or backpointers, 4 KiB per event, for reads
- * too long for a forward CTA's share of the pool); 0 = 3/5 of the free memory, at most 100 GB.
+ * too long for a forward CTA's share of the pool); 0 = 3/4 of the free memory, at most 140 GB.
  * Environment (read here, for tests): NC_STREAM_IN_MIN_EVENTS / NC_STREAM_IN_CHUNK = size from which
  * host-memory calls stream their events behind the kernel launch, and the chunk size, in events. */
 int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out);

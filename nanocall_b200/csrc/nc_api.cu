@@ -45,7 +45,10 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
     {
         size_t free_b = 0, total_b = 0;
         if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return fail("cudaMemGetInfo", e);
-        bp_pool_bytes = std::min< size_t >(free_b / 5 * 3, (size_t)100 << 30);
+        // 3/4 of the free memory, at most 140 GB: the Forward/Backward scratch (<= 24 GB) and the event arrays of a
+        // call come on top.  Long reads hold their alpha columns for their whole forward pass (a 150 k-event read:
+        // 2.4 GB for ~85 ms), so a large pool is what keeps the other forward CTAs supplied next to them.
+        bp_pool_bytes = std::min< size_t >(free_b / 4 * 3, (size_t)140 << 30);
     }
     bp_pool_bytes &= ~(size_t)4095;
     if ((e = cudaMalloc(&ctx->d_bp, bp_pool_bytes)) != cudaSuccess) return fail("cudaMalloc(backpointer pool)", e);
@@ -229,12 +232,12 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         }
     }
     // ---- which kernel decodes which job.  The alpha-column kernel is the fast path; it needs 16 KiB of scratch per
-    // event, held in one private ring per forward CTA (two consecutive jobs that fit the ring together overlap forward
-    // pass and traceback; one job may use the whole ring).  The backpointer kernel needs 4 KiB per event and one slab
-    // per CTA.  Jobs whose alpha columns fit a ring take the fast path, longer ones the backpointer kernel; when both
-    // classes exist the two kernels run concurrently on disjoint sets of SMs (every CTA of either kernel fills an SM)
-    // and disjoint parts of the pool.  A call that wants no states (candidate ranking by path probability) needs no
-    // scratch at all.
+    // event of every job between the start of its forward pass and the end of its traceback, taken from a device-wide
+    // allocator over the pool (nc_viterbi_alpha.cu), so a read of any length up to the pool takes it.  The
+    // backpointer kernel needs 4 KiB per event and one slab per CTA; it serves the reads that exceed the alpha
+    // pool (and NC_VIT_BACKPOINTER).  When both classes exist the two kernels run concurrently on disjoint sets of
+    // SMs (every CTA of either kernel fills an SM) and disjoint parts of the pool.  A call that wants no states
+    // (candidate ranking by path probability) needs no scratch at all.
     const bool want_path = states != nullptr || moves != nullptr;
     const size_t n_sms = (size_t)ctx->prop.multiProcessorCount;
     const size_t a_col = (size_t)NC_N_STATES * sizeof(float), b_col = (size_t)NC_N_STATES;
@@ -251,7 +254,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return jobs[a].n_events > jobs[b].n_events; });
     // order = [long jobs (backpointer form) | the rest (alpha form)], each longest first
     uint32_t alpha_max_len = 0xffffffffu;
-    if (want_path) alpha_max_len = (uint32_t)std::min< size_t >((ctx->bp_bytes / fwd_ctas_in(n_sms, n_jobs)) / a_col, 0xffffffffu);
+    if (want_path) alpha_max_len = (uint32_t)std::min< size_t >(ctx->bp_bytes / a_col, 0x7fffffffu);
     if (ctx->vit_mode == NC_VIT_BACKPOINTER) alpha_max_len = 0;   // forced backpointer form (tests, A/B measurements)
     uint32_t n_long = 0;
     while (n_long < n_jobs && jobs[order[n_long]].n_events > alpha_max_len) ++n_long;
@@ -291,8 +294,8 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
             tb_a = (unsigned)tb_ctas_for(fwd);
             if (want_path)
             {
-                slab_a = ((ctx->bp_bytes - pool_b) / fwd) & ~(a_col - 1);
-                // the longest alpha job must fit this (smaller) ring: otherwise it joins the backpointer class
+                slab_a = (ctx->bp_bytes - pool_b) & ~(a_col - 1);   // the alpha pool: what the backpointer slabs leave
+                // the longest alpha job must fit it: otherwise it joins the backpointer class
                 if ((size_t)jobs[order[n_long]].n_events * a_col > slab_a) { ++n_long; continue; }
             }
         }
@@ -325,6 +328,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     a.n_tb = 0;
     a.tickets = nullptr;
     a.tb_tail = a.tb_head = a.slab_free = nullptr;
+    a.colalloc = nullptr;
     a.stats = ctx->d_stats;
 
     const uint64_t base = ev_off[0];
@@ -405,15 +409,20 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         b.n_tb = tb_a;
         if (want_path)
         {
-            // tickets | tail, head | per-parity release counters of every forward CTA, zeroed
+            // tickets | tail, head | release counter of every forward CTA (zeroed) | column allocator (one free extent)
             const size_t tk_bytes = (size_t)n_short * sizeof(nc::TbTicket);
-            const size_t ctl_bytes = (2 + 2 * (size_t)fwd_a) * sizeof(unsigned);
-            if ((rc = dev_reserve(ctx, ctx->tb, tk_bytes + ctl_bytes)) != NC_OK) return rc;
+            const size_t ctl_bytes = ((2 + 2 * (size_t)fwd_a) * sizeof(unsigned) + 15) & ~(size_t)15;
+            const size_t ca_bytes = nc::viterbi_alpha_colalloc_bytes();
+            if ((rc = dev_reserve(ctx, ctx->tb, tk_bytes + ctl_bytes + ca_bytes)) != NC_OK) return rc;
             NC_CUDA(ctx, cudaMemsetAsync(ctx->tb.p, 0, tk_bytes + ctl_bytes, s));
+            ctx->colalloc_image.resize(ca_bytes);
+            nc::viterbi_alpha_colalloc_init(ctx->colalloc_image.data(), (unsigned)(slab_a / a_col));
+            NC_CUDA(ctx, cudaMemcpyAsync((char*)ctx->tb.p + tk_bytes + ctl_bytes, ctx->colalloc_image.data(), ca_bytes, cudaMemcpyHostToDevice, s));
             b.tickets = (nc::TbTicket*)ctx->tb.p;
             b.tb_tail = (unsigned*)((char*)ctx->tb.p + tk_bytes);
             b.tb_head = b.tb_tail + 1;
             b.slab_free = b.tb_tail + 2;
+            b.colalloc = (char*)ctx->tb.p + tk_bytes + ctl_bytes;
         }
         nc::viterbi_alpha_kernel<<< fwd_a + tb_a, nc::VIT_THREADS, nc::viterbi_alpha_smem_bytes(), s >>>(b);
         NC_CUDA(ctx, cudaGetLastError());

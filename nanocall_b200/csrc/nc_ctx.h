@@ -28,6 +28,7 @@ struct nc_ctx
     unsigned long long* d_landed = nullptr;
     unsigned long long* h_landed = nullptr;   // pinned: the values the copy stream writes into d_landed
     static constexpr int LANDED_SLOTS = 1024;
+    std::vector< unsigned char > colalloc_image;   // host image of the alpha kernel's column allocator (one free extent)
     uint64_t stream_in_min_events = (uint64_t)8 << 20;   // calls with fewer events copy everything before the launch
     uint64_t stream_in_chunk = (uint64_t)4 << 20;        // events per chunk of the streamed upload
     cudaDeviceProp prop;

@@ -13,10 +13,10 @@ enum { VIT_THREADS = 512 };
 struct TbTicket
 {
     unsigned job;          // index into jobs
-    unsigned slab;         // release counter of the job: 2 * forward CTA + (job parity); slab >> 1 = the CTA's ring
+    unsigned slab;         // the forward CTA that ran the job (its release counter)
     unsigned final_state;  // arg max of the last column
     unsigned ready;        // written last (release); polled with acquire
-    unsigned col0;         // first column of the job inside the ring
+    unsigned col0;         // first column of the job's extent in the pool
     unsigned pad[3];
 };
 
@@ -34,7 +34,7 @@ struct VitArgs
     const unsigned long long* landed;  // null, or the number of events already copied to the device (streamed input)
     unsigned long long ev_total;       // events in the call
     unsigned char* bp_pool;     // viterbi_kernel: gridDim.x slabs of slab_bytes of backpointers (4096 B/event);
-                                // viterbi_alpha_kernel: n_fwd rings of slab_bytes of alpha columns (16384 B/event)
+                                // viterbi_alpha_kernel: slab_bytes of alpha columns (16384 B/event), one allocator
     size_t slab_bytes;
     float* path_logprob;        // n_jobs
     unsigned short* states;     // packed like the events, may be null
@@ -42,12 +42,13 @@ struct VitArgs
     float log_2pi;              // (float)log(2*pi)  (Pore_Model.hpp:28)
     float log_n_states;         // logf(4096.f)      (Viterbi.hpp:51)
     // alpha-column kernel only: CTAs [0, n_tb) are traceback service warps fed through `tickets`, the other n_fwd
-    // CTAs run forward passes (one ring each; release counters 2*f, 2*f+1 for the jobs of even / odd parity)
+    // CTAs run forward passes (columns from the device-wide allocator; one release counter per forward CTA)
     unsigned n_fwd, n_tb;
     TbTicket* tickets;          // n_jobs entries, zeroed before the launch
     unsigned* tb_tail;          // tickets published
     unsigned* tb_head;          // tickets claimed
-    unsigned* slab_free;        // per slab: number of times a traceback released it
+    unsigned* slab_free;        // per forward CTA: number of its jobs the traceback service has released
+    void* colalloc;             // device-wide allocator of alpha columns (ColAlloc in nc_viterbi_alpha.cu)
     unsigned long long* stats;  // optional (may be null): [0] forward cycles, [1] forward cycles waiting for a slab,
                                 // [2] traceback busy cycles, [3] traceback cycles waiting for a ticket, [4] passes,
                                 // [5] lane steps, [6] jobs traced   (sums over CTAs / service warps)
@@ -57,6 +58,8 @@ __global__ void viterbi_kernel(const VitArgs a);        // backpointer form (lon
 size_t viterbi_smem_bytes();
 __global__ void viterbi_alpha_kernel(const VitArgs a);  // alpha-column form (fast path: 16 KiB/event of scratch)
 size_t viterbi_alpha_smem_bytes();
+size_t viterbi_alpha_colalloc_bytes();
+void viterbi_alpha_colalloc_init(void* host_image, unsigned pool_columns);
 
 // ---- Forward/Backward + trainer statistics
 enum { FB_EV_TILE = 16 };

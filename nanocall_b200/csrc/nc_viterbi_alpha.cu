@@ -43,6 +43,7 @@
 // across columns.  Under sustained load the GPU runs into its 1000 W power cap (SM clock 1875 of 1965 MHz).
 #include "nc_vit_common.cuh"
 
+#include <cstring>
 #include <type_traits>
 
 #ifndef NC_EXP
@@ -185,6 +186,7 @@ struct __align__(16) SmemA
     float red_v[THREADS / 32];
     int red_j[THREADS / 32];
     unsigned job;
+    unsigned col0;
     int final_state;
     unsigned long long col_bar;    // mbarrier: one phase per event column
 };
@@ -291,6 +293,136 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
     return v;
 }
 
+
+// ---------------- device-wide allocator of alpha columns.
+// The scratch pool is P columns of 16 KiB.  A job takes n consecutive columns for the time between the start of its
+// forward pass and the end of its traceback.  Free space is a sorted list of extents (first fit on allocation,
+// coalescing on release) under one lock; every operation is done by a whole warp (32 list entries per step), and
+// there are two operations per job, so the lock is idle almost always.  Compared with a fixed share of the pool per
+// forward CTA this lets a read of any length (up to the pool) take the alpha-column kernel: long reads simply hold
+// more columns while they run.  Each forward CTA keeps at most CA_MAX_LIVE jobs in flight, which bounds the list.
+constexpr int CA_MAX = 1024;
+constexpr unsigned CA_MAX_LIVE = 4;
+struct ColAlloc
+{
+    int lock;
+    unsigned n_free;
+    unsigned pad[2];
+    unsigned start[CA_MAX];   // ascending
+    unsigned len[CA_MAX];
+};
+__device__ __forceinline__ unsigned ldv(const unsigned* p) { return *reinterpret_cast< const volatile unsigned* >(p); }
+__device__ __forceinline__ void stv(unsigned* p, unsigned v) { *reinterpret_cast< volatile unsigned* >(p) = v; }
+__device__ __forceinline__ void ca_lock(ColAlloc* A, int lane)
+{
+    if (lane == 0)
+    {
+        unsigned ns = 32;
+        while (atomicCAS(&A->lock, 0, 1) != 0) { __nanosleep(ns); if (ns < 2048) ns *= 2; }
+        __threadfence();
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void ca_unlock(ColAlloc* A, int lane)
+{
+    __syncwarp();
+    if (lane == 0)
+    {
+        __threadfence();
+        atomicExch(&A->lock, 0);
+    }
+}
+// remove entry `at` of a list of nf entries (called with the lock held, by the whole warp)
+__device__ __forceinline__ void ca_remove(ColAlloc* A, unsigned at, unsigned nf, int lane)
+{
+    for (unsigned base = at; base + 1 < nf; base += 32)
+    {
+        const unsigned i = base + lane;
+        const bool have = i + 1 < nf;
+        const unsigned st = have ? ldv(A->start + i + 1) : 0u, ln = have ? ldv(A->len + i + 1) : 0u;
+        __syncwarp();
+        if (have) { stv(A->start + i, st); stv(A->len + i, ln); }
+        __syncwarp();
+    }
+    if (lane == 0) stv(&A->n_free, nf - 1);
+}
+// n columns, first fit; false when no extent is large enough right now
+__device__ __forceinline__ bool ca_alloc(ColAlloc* A, unsigned n, unsigned& s, int lane)
+{
+    ca_lock(A, lane);
+    const unsigned nf = ldv(&A->n_free);
+    int found = -1;
+    for (unsigned base = 0; base < nf; base += 32)
+    {
+        const unsigned i = base + lane;
+        const unsigned l = (i < nf) ? ldv(A->len + i) : 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, l >= n);
+        if (m) { found = (int)base + __ffs(m) - 1; break; }
+    }
+    if (found >= 0)
+    {
+        const unsigned l = ldv(A->len + found), s0 = ldv(A->start + found);
+        s = s0;
+        __syncwarp();
+        if (l > n)
+        {
+            if (lane == 0) { stv(A->start + found, s0 + n); stv(A->len + found, l - n); }
+        }
+        else ca_remove(A, (unsigned)found, nf, lane);
+    }
+    ca_unlock(A, lane);
+    return found >= 0;
+}
+__device__ __forceinline__ void ca_free(ColAlloc* A, unsigned s, unsigned n, int lane)
+{
+    ca_lock(A, lane);
+    const unsigned nf = ldv(&A->n_free);
+    unsigned idx = 0;   // number of extents below s = position of the released extent
+    for (unsigned base = 0; base < nf; base += 32)
+    {
+        const unsigned i = base + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, i < nf && ldv(A->start + i) < s);
+        idx += __popc(m);
+        if (m != 0xffffffffu) break;
+    }
+    const bool join_prev = idx > 0 && ldv(A->start + idx - 1) + ldv(A->len + idx - 1) == s;
+    const bool join_next = idx < nf && s + n == ldv(A->start + idx);
+    __syncwarp();
+    if (join_prev && join_next)
+    {
+        const unsigned add = n + ldv(A->len + idx);
+        __syncwarp();
+        if (lane == 0) stv(A->len + idx - 1, ldv(A->len + idx - 1) + add);
+        ca_remove(A, idx, nf, lane);
+    }
+    else if (join_prev)
+    {
+        if (lane == 0) stv(A->len + idx - 1, ldv(A->len + idx - 1) + n);
+    }
+    else if (join_next)
+    {
+        if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, ldv(A->len + idx) + n); }
+    }
+    else if (nf < (unsigned)CA_MAX)
+    {
+        // insert at idx: move entries idx..nf-1 up by one, top chunk first
+        for (unsigned hi = nf; hi > idx;)
+        {
+            const unsigned lo = (hi - idx > 32u) ? hi - 32u : idx;
+            const unsigned i = lo + lane;
+            const bool have = i < hi;
+            const unsigned st = have ? ldv(A->start + i) : 0u, ln = have ? ldv(A->len + i) : 0u;
+            __syncwarp();
+            if (have) { stv(A->start + i + 1, st); stv(A->len + i + 1, ln); }
+            __syncwarp();
+            hi = lo;
+        }
+        if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, n); stv(&A->n_free, nf + 1); }
+    }
+    // (a full list would leak the extent; CA_MAX_LIVE jobs per forward CTA keep it far below CA_MAX)
+    ca_unlock(A, lane);
+}
+
 __device__ __forceinline__ void forward_cta(const VitArgs& a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -302,10 +434,8 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
     const unsigned T = (unsigned)t >> 1, half = (unsigned)t & 1u;
     const bool keep = a.states != nullptr;   // path probability only: nothing to trace back, nothing stored
     unsigned jobs_done = 0;
-    // this CTA's private ring of alpha columns (slab_bytes each) and the region of its previous job
-    float* const ring = reinterpret_cast< float* >(a.bp_pool + (size_t)(blockIdx.x - a.n_tb) * a.slab_bytes);
-    const unsigned ring_cols = (unsigned)(a.slab_bytes / (NC_N_STATES * sizeof(float)));
-    unsigned prev_start = 0, prev_cols = 0;
+    ColAlloc* const CA = reinterpret_cast< ColAlloc* >(a.colalloc);
+    const unsigned fwd_id = blockIdx.x - a.n_tb;
     const float log_2pi = a.log_2pi;
     const float hl2pi = __fmul_rn(0.5f, a.log_2pi);
     const unsigned bar = smem_u32(&sm.col_bar);
@@ -328,32 +458,31 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
             if (t == 0) wait_events_landed(a, off, n);
             __syncthreads();
         }
-        // Placement of this job's n alpha columns in the ring: right after the previous job's, or at the start of
-        // the ring when they would not fit behind it (a job never wraps).  At most two jobs of a CTA are live: job
-        // k-2 must have been traced back before job k starts (release counter of parity k & 1), and job k-1 too if
-        // the new region overlaps its columns.  Two consecutive jobs that fit the ring together therefore overlap
-        // forward pass and traceback, and a single job may use the whole ring.
-        const unsigned slab_id = 2u * (blockIdx.x - a.n_tb) + (jobs_done & 1u);
-        unsigned col0 = prev_start + prev_cols;
-        if (col0 + n > ring_cols) col0 = 0;
-        const bool hits_prev = jobs_done >= 1 && col0 < prev_start + prev_cols && prev_start < col0 + n;
-        float* const acol = ring + (size_t)col0 * NC_N_STATES;
-        if (keep && jobs_done >= 1)
+        // The job's n alpha columns: one extent of the pool (ca_alloc), held until the traceback service releases it.
+        // The CTA keeps at most CA_MAX_LIVE jobs in flight (the service counts its releases in slab_free[fwd_id]).
+        unsigned col0 = 0;
+        if (keep)
         {
-            if (t == 0)
+            if (warp == 0)
             {
                 const long long c0 = clock64();
                 unsigned ns = 64;
-                if (jobs_done >= 2)
-                    while (ld_acquire_u32(a.slab_free + slab_id) < (jobs_done >> 1)) { __nanosleep(ns); if (ns < 4096) ns *= 2; }
-                if (hits_prev)
-                    while (ld_acquire_u32(a.slab_free + (slab_id ^ 1u)) < ((jobs_done - 1) >> 1) + 1u) { __nanosleep(ns); if (ns < 4096) ns *= 2; }
-                if (a.stats) atomicAdd(a.stats + 1, (unsigned long long)(clock64() - c0));
+                if (lane == 0)
+                    while (ld_acquire_u32(a.slab_free + fwd_id) + CA_MAX_LIVE <= jobs_done) { __nanosleep(ns); if (ns < 4096) ns *= 2; }
+                __syncwarp();
+                unsigned got = 0;
+                ns = 128;
+                while (!ca_alloc(CA, n, got, lane)) { __nanosleep(ns); if (ns < 8192) ns *= 2; }
+                if (lane == 0)
+                {
+                    sm.col0 = got;
+                    if (a.stats) atomicAdd(a.stats + 1, (unsigned long long)(clock64() - c0));
+                }
             }
             __syncthreads();
+            col0 = sm.col0;
         }
-        prev_start = col0;
-        prev_cols = n;
+        float* const acol = reinterpret_cast< float* >(a.bp_pool) + (size_t)col0 * NC_N_STATES;
         const long long fwd_c0 = clock64();
 
         // ---------------- prologue: scaled model constants (as state pairs) and transition weights
@@ -560,8 +689,8 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
         }
 
         // ---------------- hand the traceback to a service warp (other CTAs of this grid) and go on with the next job.
-        // The alpha columns of this job stay in the ring until the service warp releases them (counter slab_id), so
-        // the forward pass of job k+1 overlaps the traceback of job k.
+        // The alpha columns of this job stay allocated until the service warp releases them, so the forward pass of
+        // job k+1 overlaps the traceback of job k.
         if (keep)
         {
             __threadfence();        // every thread: its alpha stores are visible device-wide before the ticket is
@@ -571,7 +700,7 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
                 const unsigned slot = atomicAdd(a.tb_tail, 1u);
                 TbTicket& tk = a.tickets[slot];
                 tk.job = job_idx;
-                tk.slab = slab_id;
+                tk.slab = fwd_id;
                 tk.col0 = col0;
                 tk.final_state = (unsigned)sm.final_state;
                 __threadfence();
@@ -613,7 +742,7 @@ __device__ void traceback_service(const VitArgs& a)
         const DevJob& J = a.jobs[job_idx];
         const unsigned n = J.n_events;
         const float* lut = J.lut;
-        const float* acol = reinterpret_cast< const float* >(a.bp_pool + (size_t)(slab_id >> 1) * a.slab_bytes) + (size_t)col0 * NC_N_STATES;
+        const float* acol = reinterpret_cast< const float* >(a.bp_pool) + (size_t)col0 * NC_N_STATES;
         unsigned short* out_s = a.states + J.ev_off;
         const unsigned T = n - 1;  // transitions: column c in 1..T is entered from column c-1
         if (T == 0)
@@ -663,7 +792,8 @@ __device__ void traceback_service(const VitArgs& a)
         }
         __threadfence();   // states visible to the lanes that derive the moves; slab reads are complete
         __syncwarp();
-        if (lane == 0) atomicAdd(a.slab_free + slab_id, 1u);
+        ca_free(reinterpret_cast< ColAlloc* >(a.colalloc), col0, n, lane);
+        if (lane == 0) atomicAdd(a.slab_free + slab_id, 1u);   // slab_id = the forward CTA that ran the job
         if (a.stats)
         {
             for (int d = 16; d > 0; d >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, d);
@@ -696,5 +826,14 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
 }
 
 size_t viterbi_alpha_smem_bytes() { return sizeof(SmemA); }
+size_t viterbi_alpha_colalloc_bytes() { return sizeof(ColAlloc); }
+void viterbi_alpha_colalloc_init(void* host_image, unsigned pool_columns)
+{
+    ColAlloc* A = static_cast< ColAlloc* >(host_image);
+    memset(A, 0, sizeof(ColAlloc));
+    A->n_free = 1;
+    A->start[0] = 0;
+    A->len[0] = pool_columns;
+}
 
 } // namespace nc

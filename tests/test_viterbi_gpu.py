@@ -207,13 +207,31 @@ def test_mixed_dispatch_small_pool(port, models, vit_mode):
         pytest.skip("dispatch test runs once")
     table = models[R73T]["table"]
     lengths = [3000, 40, 900, 2500, 200, 100]
-    # 6 CTAs wanted; 3000 events need 12.3 MB of backpointers, a slab of pool/6 = 16 MiB holds 1024 alpha columns
-    c = api.Context(0, bp_pool_bytes=96 << 20)
+    # a 32 MiB pool holds 2048 alpha columns: the 3000- and 2500-event jobs take the backpointer kernel (2 slabs of
+    # 12.3 MB), which leaves 548 columns, so the 900-event job joins them; 200, 100 and 40 take the alpha kernel
+    c = api.Context(0, bp_pool_bytes=32 << 20)
     try:
         mid = c.register_model(table, 0)
         batch = synth.make_batch(51, table, lengths)
         _check_batch(c, port, table, mid, batch, None, None)
         assert c.last_launches() == 2
+    finally:
+        c.close()
+
+
+def test_column_allocator_under_pressure(port, models, vit_mode):
+    """Alpha kernel with a pool that holds only ~6 of the 40 jobs at a time: forward CTAs wait for columns, the
+    traceback service releases and coalesces extents of different sizes; same bits as the oracle."""
+    if vit_mode != "alpha":
+        pytest.skip("allocator test runs once")
+    table = models[R73T]["table"]
+    lengths = [1500, 90, 700, 1100, 33, 400, 1300, 250, 999, 64] * 4
+    c = api.Context(0, bp_pool_bytes=100 << 20)   # 6400 columns
+    try:
+        mid = c.register_model(table, 0)
+        batch = synth.make_batch(57, table, lengths)
+        _check_batch(c, port, table, mid, batch, None, None)
+        assert c.last_launches() == 1
     finally:
         c.close()
 
