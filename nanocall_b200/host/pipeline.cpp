@@ -50,10 +50,15 @@ static nc_pm_params default_pm()
     return p;
 }
 
-Pipeline::Pipeline(const Options& o, int device) : opt_(o)
+Pipeline::Pipeline(const Options& o, int device, size_t viterbi_events_hint) : opt_(o)
 {
     if (opt_.train_drift < 0) opt_.train_drift = (opt_.pore == "r73") ? 1 : 0;  // nanocall.cpp:943-969
-    int rc = nc_ctx_create(device, 0, &ctx_);
+    // Viterbi scratch: 16 KiB per event of the jobs in flight.  A shard that cannot use the default pool (3/4 of the
+    // free memory, up to seconds of cudaMalloc) asks for what it can use.
+    size_t pool = 0;
+    if (viterbi_events_hint) pool = std::max< size_t >((size_t)1 << 30, viterbi_events_hint * 16384u + ((size_t)256 << 20));
+    int rc = nc_ctx_create(device, pool, &ctx_);
+    if (rc == NC_ERR_CUDA && pool) rc = nc_ctx_create(device, 0, &ctx_);   // larger than the device: take the default
     if (rc != NC_OK) throw std::runtime_error(std::string("nc_ctx_create: ") + nc_last_error(nullptr));
 }
 

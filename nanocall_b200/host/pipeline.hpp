@@ -80,7 +80,7 @@ struct Model
 class Pipeline
 {
 public:
-    Pipeline(const Options& o, int device);
+    Pipeline(const Options& o, int device, size_t viterbi_events_hint = 0);
     ~Pipeline();
     Pipeline(const Pipeline&) = delete;
     Pipeline& operator=(const Pipeline&) = delete;
