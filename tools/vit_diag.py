@@ -17,13 +17,20 @@ def main():
     ap.add_argument("--reads", type=int, default=4000)
     ap.add_argument("--events", type=int, default=10000)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--seed", type=int, default=11)
+    ap.add_argument("--mix", action="store_true", help="read-length mixture of configs[4] instead of --events per read")
     args = ap.parse_args()
     import torch
     from nanocall_b200 import api, models, synth
 
     table = models.builtin_model("r73.t")["table"]
-    batch = synth.make_batch_uniform(11, table, args.reads, args.events)
-    total = args.reads * args.events
+    if args.mix:
+        lengths = synth.mixture_lengths(args.seed, args.reads)
+        batch = synth.make_batch_uniform(args.seed, table, 0, 0, lengths=lengths)
+        total = int(lengths.sum())
+    else:
+        batch = synth.make_batch_uniform(11, table, args.reads, args.events)
+        total = args.reads * args.events
     dev = torch.device("cuda", 0)
     ctx = api.Context(0)
     mid = ctx.register_model(table, 0)
@@ -42,7 +49,7 @@ def main():
             ms = ctx.last_kernel_ms()
             st = ctx.viterbi_stats(reset=True)
             out = {"mode": tag, "ms": ms, "events_per_s": total / ms * 1e3, **st}
-            n_fwd = 144 if states else 148
+            n_fwd = 145 if states else 148
             out["fwd_busy_frac"] = st["fwd_cycles"] / (n_fwd * ms * 1e-3 * sm_hz)
             out["cycles_per_column"] = st["fwd_cycles"] / total
             if states:
