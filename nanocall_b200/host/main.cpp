@@ -229,7 +229,7 @@ int main(int argc, char** argv)
             auto secs_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration< double >(now() - t).count(); };
             auto w0 = now();
             // events that can be in flight in one Viterbi call: every job of the shard (two candidate models per
-            // strand at most), but no more than ~600 jobs (148 CTAs x 4) of the longest strand
+            // strand at most), but no more than ~300 jobs (2 per forward CTA) of the longest strand
             size_t shard_events = 0, longest = 0;
             for (size_t i = bounds[g]; i < bounds[g + 1]; ++i)
                 for (unsigned st = 0; st < 2; ++st)
@@ -237,7 +237,7 @@ int main(int argc, char** argv)
                     shard_events += reads[i].events[st].size();
                     longest = std::max(longest, reads[i].events[st].size());
                 }
-            Pipeline p(cli.opt, cli.first_device + g, std::min(2 * shard_events, 600 * longest));
+            Pipeline p(cli.opt, cli.first_device + g, std::min(2 * shard_events, 300 * longest));
             p.init_models();
             std::vector< Read* > mine;
             for (size_t i = bounds[g]; i < bounds[g + 1]; ++i)

@@ -19,6 +19,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:viterbi_alpha -c 1 -f -o $out/vit_alpha \
     python bench.py --reads 1480 --events 3000 --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $out/ncu_full.log 2>&1
 tail -2 $out/ncu_full.log
+python bench.py --mix --reads 4000 --no-cpu-baseline > $out/bench_mix.json 2>> $out/bench.err
+cut -c1-160 $out/bench_mix.json
 bash tools/pipeline_bench.sh $out 1000 5000 5000 > $out/pipeline.json 2> $out/pipeline.err
 cat $out/pipeline.json
 python tools/make_synth_ncev.py /tmp/pipe_small.ncev 64 5000 5000 7 > /dev/null
