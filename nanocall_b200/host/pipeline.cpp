@@ -648,6 +648,17 @@ void Pipeline::write_stats(std::ostream& os, const Read& r) const
 }
 
 // ---------------------------------------------------------------- event tables
+// Fast5_Summary::filter_ed_event (Fast5_Summary.hpp:734-745): the reference drops an eventdetection event whose mean
+// reaches the abasic level or whose stdv exceeds 4 before it builds the strands' event sequences (:352-363).  Event
+// tables are the input here, so the same rule is applied on load; the abasic level is known only when the table
+// carries it ("#abasic_level <pA>"), otherwise that half of the rule is off.
+static bool keep_event(float mean, float stdv, float abasic_level)
+{
+    if (mean >= abasic_level) return false;
+    if (stdv > 4.0f) return false;
+    return true;
+}
+
 bool load_events_tsv(const std::string& path, Read& r, std::string& err)
 {
     // "#read_id <id>" header (optional), then rows "strand mean stdv start length"; the last four columns are what
@@ -667,6 +678,7 @@ bool load_events_tsv(const std::string& path, Read& r, std::string& err)
         }
     }
     r.read_id = r.base_file_name;
+    float abasic_level = std::numeric_limits< float >::infinity();
     std::string line;
     while (std::getline(is, line))
     {
@@ -677,12 +689,14 @@ bool load_events_tsv(const std::string& path, Read& r, std::string& err)
             std::string k, v;
             iss >> k >> v;
             if (k == "read_id" && !v.empty()) r.read_id = v;
+            if (k == "abasic_level" && !v.empty()) abasic_level = std::strtof(v.c_str(), nullptr);
             continue;
         }
         std::istringstream iss(line);
         unsigned st;
         float mean, stdv, start, length;
         if (!(iss >> st >> mean >> stdv >> start >> length) || st > 1) { err = "bad event row in " + path + ": " + line; return false; }
+        if (!keep_event(mean, stdv, abasic_level)) continue;
         Strand_Events& ev = r.events[st];
         ev.mean.push_back(mean); ev.stdv.push_back(stdv); ev.start.push_back(start); ev.length.push_back(length);
     }
@@ -723,6 +737,18 @@ bool load_events_ncev(const std::string& path, std::vector< Read >& reads, std::
             }
         }
         if (!is) { err = "truncated " + path; return false; }
+        for (int st = 0; st < 2; ++st)   // the stdv half of filter_ed_event (the container carries no abasic level)
+        {
+            Strand_Events& ev = r.events[st];
+            size_t w = 0;
+            for (size_t i = 0; i < ev.mean.size(); ++i)
+                if (keep_event(ev.mean[i], ev.stdv[i], std::numeric_limits< float >::infinity()))
+                {
+                    ev.mean[w] = ev.mean[i]; ev.stdv[w] = ev.stdv[i]; ev.start[w] = ev.start[i]; ev.length[w] = ev.length[i];
+                    ++w;
+                }
+            for (std::vector< float >* v : { &ev.mean, &ev.stdv, &ev.start, &ev.length }) v->resize(w);
+        }
         reads.push_back(std::move(r));
     }
     return true;

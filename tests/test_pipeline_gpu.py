@@ -114,6 +114,15 @@ def test_events_tsv_input(tmp_path, port, models):
     rd = _make_reads(models, 9, 1, nt=300, nc=250)[0]
     path = os.path.join(str(tmp_path), "one.events.tsv")
     evio.write_events_tsv(path, "tsvread", rd[1])
+    # the reference's event filter (Fast5_Summary.hpp:734-745) is applied on load: an event whose stdv exceeds 4 or whose
+    # mean reaches the table's abasic level is dropped, so these three rows must leave the calls unchanged
+    lines = open(path).read().split("\n")
+    first = next(k for k, l in enumerate(lines) if l and not l.startswith("#"))
+    lines.insert(first + 5, "0\t61.5\t4.25\t0.1111\t0.01")
+    lines.insert(first + 40, "0\t250.0\t1.0\t0.7777\t0.01")
+    lines.insert(first, "#abasic_level 200.0")
+    lines.append("1\t55.0\t9.0\t99.0\t0.01")
+    open(path, "w").write("\n".join(lines) + "\n")
     out = os.path.join(str(tmp_path), "o.fa")
     p = subprocess.run([CLI, "--pore", "r73", "--no-train", "-o", out, "--log", "warning", str(tmp_path)],
                        capture_output=True, text=True, timeout=300)
