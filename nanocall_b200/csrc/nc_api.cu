@@ -446,6 +446,37 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         a.moves = moves ? moves + base : nullptr;
     }
 
+    if (stream_in)
+    {
+        // Queue the chunked upload on the copy stream BEFORE the kernels are launched: the copies are asynchronous
+        // (pinned memory) so the launch follows at once and the kernels overlap them, and nothing can deadlock when
+        // launches are serialised (profilers, CUDA_LAUNCH_BLOCKING, pageable buffers): the data is then simply
+        // there first.  Chunks are multiples of 32 events (whole 128-byte lines).
+        cudaStream_t sc = ctx->stream3;
+        NC_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev3, 0));
+        const float* lsp = log_stdv ? log_stdv + base : nullptr;
+        uint64_t chunk = std::max< uint64_t >(ctx->stream_in_chunk, (total + nc_ctx::LANDED_SLOTS - 1) / nc_ctx::LANDED_SLOTS);
+        chunk = (chunk + 31) & ~(uint64_t)31;
+        int slot = 0;
+        cudaError_t ce = cudaSuccess;
+        for (uint64_t c0 = 0; c0 < total && ce == cudaSuccess; c0 += chunk, ++slot)
+        {
+            const uint64_t c1 = std::min(total, c0 + chunk), nb = (c1 - c0) * sizeof(float);
+            ce = cudaMemcpyAsync((float*)ctx->mean.p + c0, mean + base + c0, nb, cudaMemcpyHostToDevice, sc);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync((float*)ctx->stdv.p + c0, stdv + base + c0, nb, cudaMemcpyHostToDevice, sc);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync((float*)ctx->start.p + c0, start + base + c0, nb, cudaMemcpyHostToDevice, sc);
+            if (ce == cudaSuccess && lsp) ce = cudaMemcpyAsync((float*)ctx->lstd.p + c0, lsp + c0, nb, cudaMemcpyHostToDevice, sc);
+            ctx->h_landed[slot] = c1;
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(ctx->d_landed, ctx->h_landed + slot, sizeof(unsigned long long), cudaMemcpyHostToDevice, sc);
+        }
+        if (ce != cudaSuccess)
+        {
+            cudaStreamSynchronize(sc);
+            cudaStreamSynchronize(s);
+            NC_FAIL(ctx, NC_ERR_CUDA, "nc_viterbi_packed: streamed event upload failed: %s", cudaGetErrorString(ce));
+        }
+    }
     NC_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     ctx->last_launches = 0;
     if (n_long)
@@ -489,37 +520,6 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         NC_CUDA(ctx, cudaGetLastError());
         ++ctx->last_launches;
         if (n_long) NC_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev2, 0));
-    }
-    if (stream_in)
-    {
-        // the kernels are queued; now feed them.  Chunks are multiples of 32 events (whole 128-byte lines).
-        cudaStream_t sc = ctx->stream3;
-        NC_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev3, 0));
-        const float* lsp = log_stdv ? log_stdv + base : nullptr;
-        uint64_t chunk = std::max< uint64_t >(ctx->stream_in_chunk, (total + nc_ctx::LANDED_SLOTS - 1) / nc_ctx::LANDED_SLOTS);
-        chunk = (chunk + 31) & ~(uint64_t)31;
-        int slot = 0;
-        cudaError_t ce = cudaSuccess;
-        for (uint64_t c0 = 0; c0 < total && ce == cudaSuccess; c0 += chunk, ++slot)
-        {
-            const uint64_t c1 = std::min(total, c0 + chunk), nb = (c1 - c0) * sizeof(float);
-            ce = cudaMemcpyAsync((float*)ctx->mean.p + c0, mean + base + c0, nb, cudaMemcpyHostToDevice, sc);
-            if (ce == cudaSuccess) ce = cudaMemcpyAsync((float*)ctx->stdv.p + c0, stdv + base + c0, nb, cudaMemcpyHostToDevice, sc);
-            if (ce == cudaSuccess) ce = cudaMemcpyAsync((float*)ctx->start.p + c0, start + base + c0, nb, cudaMemcpyHostToDevice, sc);
-            if (ce == cudaSuccess && lsp) ce = cudaMemcpyAsync((float*)ctx->lstd.p + c0, lsp + c0, nb, cudaMemcpyHostToDevice, sc);
-            ctx->h_landed[slot] = c1;
-            if (ce == cudaSuccess)
-                ce = cudaMemcpyAsync(ctx->d_landed, ctx->h_landed + slot, sizeof(unsigned long long), cudaMemcpyHostToDevice, sc);
-        }
-        if (ce != cudaSuccess)
-        {
-            // never leave the kernels waiting for events that will not come: declare everything landed, drain, fail
-            ctx->h_landed[0] = total;
-            cudaMemcpyAsync(ctx->d_landed, ctx->h_landed, sizeof(unsigned long long), cudaMemcpyHostToDevice, sc);
-            cudaStreamSynchronize(sc);
-            cudaStreamSynchronize(s);
-            NC_FAIL(ctx, NC_ERR_CUDA, "nc_viterbi_packed: streamed event upload failed: %s", cudaGetErrorString(ce));
-        }
     }
     NC_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
 

@@ -358,6 +358,7 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
 
     uint32_t g0 = 0;
     std::vector< float > lz, pm_rows, st_acc;
+    float kernel_ms = 0.f;   // device time of the call = sum over its waves
     while (g0 < n_groups)
     {
         // ---- a wave: consecutive groups whose slabs fit the scratch pool
@@ -402,6 +403,7 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
                            nullptr, opts->train_scaling != 0, opts->train_transitions != 0,
                            lz, pm_rows, st_acc)) != NC_OK)
             return rc;
+        kernel_ms += ctx->last_kernel_ms;
         // ---- finish every group of the wave on the host (train_one_round, :541-579)
         for (uint32_t g = g0; g < g1; ++g)
         {
@@ -434,6 +436,7 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
         }
         g0 = g1;
     }
+    ctx->last_kernel_ms = kernel_ms;
     return NC_OK;
 }
 
