@@ -72,8 +72,8 @@ __device__ __forceinline__ void st_cs_v8(float* p, const float (&v)[8])
 // emission keeps the reference's bits (tests/test_viterbi_gpu.py runs every case through this kernel).
 typedef unsigned long long f2;
 __device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ float lo_of(f2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); (void)b; return a; }
-__device__ __forceinline__ float hi_of(f2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); (void)a; return b; }
+__device__ __forceinline__ float lo_of(f2 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi_of(f2 v) { return __uint_as_float((unsigned)(v >> 32)); }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
@@ -533,7 +533,7 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
 
         // publish<B>: from column i-1 (a_own) the weighted class candidates of column i into buffer B; stream
         // column i-1 to the slab; arrive on the column barrier
-        f2 a_own[SPT / 2];
+        f2 a_own[SPT / 2] = { 0, 0, 0, 0 };   // (set by column 0 below, before the first publish)
         auto publish = [&](auto buf_tag) {
             constexpr unsigned B = decltype(buf_tag)::value;
             const float m1a = max3(fmaxf(lo_of(a_own[0]), hi_of(a_own[0])), lo_of(a_own[1]), hi_of(a_own[1]));
