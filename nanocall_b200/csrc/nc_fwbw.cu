@@ -112,7 +112,6 @@ __device__ __forceinline__ float fold_logsum_in_order(float acc, const int n, Ge
 
 struct StSmem
 {
-    float tbl[16000];
     float term[2][3][ST_CHUNK];   // two buffers: computed by warps 3..15, folded by warps 0..2
     float lst[3][FOLD_LIST];
 };
@@ -517,9 +516,10 @@ __global__ void __launch_bounds__(FB_THREADS) st_stats_kernel(const FbArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StSmem& ss = *reinterpret_cast< StSmem* >(smem_raw);
-    float* tbl = ss.tbl;
+    // the p7_FLogsum table stays in global memory here: with 11 KB of shared memory per CTA four CTAs fit an SM
+    // (the kernel is latency-bound by its sequential folds) and the 64 KB table lives in the L1 the carve-out leaves
+    const float* __restrict__ tbl = a.logsum_tbl;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    for (int q = t; q < 16000; q += FB_THREADS) tbl[q] = a.logsum_tbl[q];
     const unsigned grp = blockIdx.x;
     const unsigned st = blockIdx.y;
     const FbGroup& G = a.groups[grp];
@@ -582,7 +582,6 @@ __global__ void __launch_bounds__(FB_THREADS) st_stats_kernel(const FbArgs a)
         term[2][ct] = t_skip;
     };
 
-    __syncthreads();   // tbl
     Cursor cc = { G.seq_begin, 0, 0 };
     skip(cc);
     if (valid(cc) && warp >= 3) compute(cc, ss.term[0]);
