@@ -174,10 +174,24 @@ def run_reference(args, rank, world):
             "cpu_baseline": res,
             "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_OUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    print(json.dumps(line), file=_OUT or sys.stdout, flush=True)
 
 
 def main():
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL prints its version at the first
+    # collective) goes to stderr instead; the line itself is written to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -338,7 +352,7 @@ def main():
                            "timing": "wall clock around nc_viterbi_packed(NC_MEM_HOST), pinned buffers"}
         if world == 1 and not args.no_cpu_baseline and not args.mix:   # (a 150k-event read needs 4.9 GB per CPU thread)
             line["cpu_baseline"], _ = cpu_baseline(table, batch, args.events, args.cpu_sample_reads)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
