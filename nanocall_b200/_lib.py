@@ -68,6 +68,7 @@ SYMBOLS = {
     "nc_mean_stdv": (None, [_u32, _vp, C.POINTER(_f), C.POINTER(_f)]),
     "nc_transition_lut": (None, [_f, _f, _vp]),
     "nc_min_skip": (_u32, [_u32, _u32]),
+    "nc_plan_dispatch_order": (C.c_int, [_u32, _vp, C.c_uint64, _u32, _vp]),
     "nc_version": (C.c_char_p, []),
 }
 

@@ -8,8 +8,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
-#include <queue>
-#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -305,61 +303,16 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     }
     const uint32_t n_short = n_jobs - n_long;
 
-    // ---- dispatch order of the alpha class.  Longest-first balances the forward CTAs, but it starts all the long
-    // reads at once and they pin their columns for their whole forward pass: measured on the configs[4] mixture,
-    // forward CTAs then wait for columns 14 % of the time.  So the order is the one a simulated run of the launch
-    // produces with the rule "the longest job whose columns are free now" (fwd_a workers, time proportional to
-    // the events of a job, columns held until the job ends plus a margin for its traceback, 90 % of the pool to allow
-    // for fragmentation): longest-first whenever memory allows, shorter jobs while it is tight.
+    // ---- dispatch order of the alpha class (nc_plan_dispatch_order, nc_host.cpp): longest-first whenever the pool
+    // allows, shorter jobs while the long reads pin most of it
     if (want_path && n_short > fwd_a && fwd_a > 0)
     {
-        const uint64_t pool_cols = (uint64_t)((double)(slab_a / a_col) * 0.9);
-        uint64_t need_first = 0;
-        for (uint32_t k = 0; k < fwd_a; ++k) need_first += jobs[order[n_long + k]].n_events;
-        if (need_first * 11 / 10 > pool_cols)   // only when the first wave does not simply fit
+        std::vector< uint32_t > lens(n_short), perm(n_short);
+        for (uint32_t k = 0; k < n_short; ++k) lens[k] = jobs[order[n_long + k]].n_events;
+        if (nc_plan_dispatch_order(n_short, lens.data(), (uint64_t)(slab_a / a_col), fwd_a, perm.data()))
         {
-            std::multiset< std::pair< unsigned, unsigned > > remaining;   // (length, position in order): ascending
-            for (uint32_t k = 0; k < n_short; ++k) remaining.insert({ jobs[order[n_long + k]].n_events, n_long + k });
-            typedef std::pair< double, unsigned > Fin;                   // (finish time, columns)
-            std::priority_queue< Fin, std::vector< Fin >, std::greater< Fin > > running;
-            std::vector< unsigned > seq;
-            seq.reserve(n_short);
-            uint64_t free_cols = pool_cols;
-            unsigned idle = fwd_a;
-            double now = 0.0;
-            while (!remaining.empty())
-            {
-                bool placed = false;
-                if (idle > 0)
-                {
-                    auto it = remaining.upper_bound({ (unsigned)std::min< uint64_t >(free_cols, 0xffffffffu), 0xffffffffu });
-                    if (it != remaining.begin())
-                    {
-                        --it;   // the longest job that fits; among equals the one latest in the original order
-                        const unsigned len = it->first;
-                        seq.push_back(order[it->second]);
-                        remaining.erase(it);
-                        free_cols -= len;
-                        --idle;
-                        running.push({ now + 1.1 * (double)len, len });
-                        placed = true;
-                    }
-                }
-                if (!placed)
-                {
-                    if (running.empty())   // a job larger than 90 % of the pool: runs alone, in the original order
-                    {
-                        auto it = std::prev(remaining.end());
-                        seq.push_back(order[it->second]);
-                        remaining.erase(it);
-                        continue;
-                    }
-                    now = running.top().first;
-                    free_cols += running.top().second;
-                    ++idle;
-                    running.pop();
-                }
-            }
+            std::vector< unsigned > seq(n_short);
+            for (uint32_t k = 0; k < n_short; ++k) seq[k] = order[n_long + perm[k]];
             std::copy(seq.begin(), seq.end(), order.begin() + n_long);
         }
     }

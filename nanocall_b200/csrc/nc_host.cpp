@@ -5,6 +5,8 @@
 #include "nc_internal.h"
 
 #include <cmath>
+#include <set>
+#include <queue>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -113,6 +115,65 @@ void nc_transition_lut(float p_stay, float p_skip, float* lut64)
         p += tail;
         lut64[mask] = std::log(p);
     }
+}
+
+// Dispatch order of the alpha-column kernel's jobs.  lens[] is sorted descending (longest-first balances the forward
+// CTAs), but that order starts all the long reads at once and they pin their alpha columns for their whole forward
+// pass: measured on the configs[4] mixture, forward CTAs then wait for columns 14 % of the time.  The order returned
+// is the one a simulated run of the launch produces with the rule "the longest job whose columns are free now"
+// (n_workers forward CTAs, time proportional to the events of a job, columns held until the job ends plus a margin
+// for its traceback, 90 % of the pool to allow for fragmentation): longest-first whenever memory allows, shorter
+// jobs while it is tight.  perm[k] = index into lens[] of the k-th job to dispatch.  Returns 0 (perm = identity)
+// when the first wave simply fits.
+int nc_plan_dispatch_order(uint32_t n_jobs, const uint32_t* lens, uint64_t pool_columns, uint32_t n_workers, uint32_t* perm)
+{
+    for (uint32_t k = 0; k < n_jobs; ++k) perm[k] = k;
+    if (n_jobs == 0 || n_workers == 0 || n_jobs <= n_workers) return 0;
+    const uint64_t pool_cols = (uint64_t)((double)pool_columns * 0.9);
+    uint64_t need_first = 0;
+    for (uint32_t k = 0; k < n_workers; ++k) need_first += lens[k];
+    if (need_first * 11 / 10 <= pool_cols) return 0;
+    std::multiset< std::pair< uint32_t, uint32_t > > remaining;   // (length, index): ascending
+    for (uint32_t k = 0; k < n_jobs; ++k) remaining.insert({ lens[k], k });
+    typedef std::pair< double, uint32_t > Fin;                    // (finish time, columns)
+    std::priority_queue< Fin, std::vector< Fin >, std::greater< Fin > > running;
+    uint64_t free_cols = pool_cols;
+    uint32_t idle = n_workers, out = 0;
+    double now = 0.0;
+    while (!remaining.empty())
+    {
+        bool placed = false;
+        if (idle > 0)
+        {
+            auto it = remaining.upper_bound({ (uint32_t)std::min< uint64_t >(free_cols, 0xffffffffu), 0xffffffffu });
+            if (it != remaining.begin())
+            {
+                --it;   // the longest job that fits
+                const uint32_t len = it->first;
+                perm[out++] = it->second;
+                remaining.erase(it);
+                free_cols -= len;
+                --idle;
+                running.push({ now + 1.1 * (double)len, len });
+                placed = true;
+            }
+        }
+        if (!placed)
+        {
+            if (running.empty())   // a job larger than 90 % of the pool: it runs alone
+            {
+                auto it = std::prev(remaining.end());
+                perm[out++] = it->second;
+                remaining.erase(it);
+                continue;
+            }
+            now = running.top().first;
+            free_cols += running.top().second;
+            ++idle;
+            running.pop();
+        }
+    }
+    return 1;
 }
 
 // Kmer::min_skip (Kmer.hpp:51-68)

@@ -67,3 +67,42 @@ def test_mean_stdv_base_seq_min_skip():
         for i in range(1, min(st.size, 400)):
             assert lib.nc_min_skip(int(st[i - 1]), int(st[i])) == int(mv[i])
     assert api.base_seq(np.array([0x1B], np.uint16), np.array([0], np.uint8)) == "AAACGT"
+
+
+def test_dispatch_order_planner():
+    """nc_plan_dispatch_order (host helper behind nc_viterbi_packed): a permutation; identity when the first wave fits
+    the pool; otherwise the memory of the jobs running at any time of the simulated schedule stays within the pool,
+    and the longest job still starts first."""
+    import ctypes as C
+    from nanocall_b200 import _lib, synth
+    lib = _lib.load()
+    lens = np.sort(synth.mixture_lengths(2026, 4000).astype(np.uint32))[::-1].copy()
+    perm = np.zeros(lens.size, np.uint32)
+    pool, workers = 8_000_000, 145
+    changed = lib.nc_plan_dispatch_order(lens.size, lens.ctypes.data, C.c_uint64(pool), workers, perm.ctypes.data)
+    assert changed == 1
+    assert np.array_equal(np.sort(perm), np.arange(lens.size, dtype=np.uint32))
+    assert perm[0] == 0                                   # the longest read starts first
+    # replay an order with the planner's timing and memory model (a job starts when a forward CTA is idle and its
+    # columns are free): the planned order finishes no later than plain longest-first
+    import heapq
+
+    def replay(order):
+        running, free, idle, now, end = [], int(pool * 0.9), workers, 0.0, 0.0
+        for k in order:
+            n = int(lens[k])
+            while idle == 0 or n > free:
+                t, m = heapq.heappop(running)
+                now, free, idle = t, free + m, idle + 1
+            free, idle = free - n, idle - 1
+            heapq.heappush(running, (now + 1.1 * n, n))
+            end = max(end, now + 1.1 * n)
+        return end
+
+    planned, lpt = replay(perm), replay(np.arange(lens.size))
+    assert planned <= lpt, (planned, lpt)
+    # a batch whose first wave fits keeps longest-first
+    small = np.full(1000, 10000, np.uint32)
+    p2 = np.zeros(small.size, np.uint32)
+    assert lib.nc_plan_dispatch_order(small.size, small.ctypes.data, C.c_uint64(pool), workers, p2.ctypes.data) == 0
+    assert np.array_equal(p2, np.arange(small.size, dtype=np.uint32))
