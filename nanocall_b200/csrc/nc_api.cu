@@ -132,6 +132,7 @@ int nc_ctx_viterbi_stats(nc_ctx* ctx, uint64_t* out8, int reset)
 int nc_ctx_sync(nc_ctx* ctx)
 {
     if (!ctx) return NC_ERR_ARG;
+    NC_CUDA(ctx, cudaSetDevice(ctx->device));
     NC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NC_OK;
 }
@@ -322,10 +323,51 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     if ((rc = dev_reserve(ctx, ctx->order, n_jobs * sizeof(unsigned))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->counter, 2 * sizeof(unsigned))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->path, n_jobs * sizeof(float))) != NC_OK) return rc;
+    // alpha kernel control block: tickets | tail, head | release counter of every forward CTA | column allocator.
+    // Every allocation of the call happens before its first asynchronous operation (a cudaFree inside dev_reserve is a
+    // device-wide synchronisation, and an allocation failure must not leave copies or kernels in flight).
+    const size_t tk_bytes = (size_t)n_short * sizeof(nc::TbTicket);
+    const size_t ctl_bytes = ((2 + 2 * (size_t)fwd_a) * sizeof(unsigned) + 15) & ~(size_t)15;
+    const size_t ca_bytes = nc::viterbi_alpha_colalloc_bytes();
+    if (n_short && want_path && (rc = dev_reserve(ctx, ctx->tb, tk_bytes + ctl_bytes + ca_bytes)) != NC_OK) return rc;
+    const uint64_t base = ev_off[0];
+    bool stream_in = false;
+    if (mem == NC_MEM_HOST)
+    {
+        if ((rc = dev_reserve(ctx, ctx->mean, total * sizeof(float))) != NC_OK) return rc;
+        if ((rc = dev_reserve(ctx, ctx->stdv, total * sizeof(float))) != NC_OK) return rc;
+        if ((rc = dev_reserve(ctx, ctx->start, total * sizeof(float))) != NC_OK) return rc;
+        if (log_stdv && (rc = dev_reserve(ctx, ctx->lstd, total * sizeof(float))) != NC_OK) return rc;
+        if ((states || moves) && (rc = dev_reserve(ctx, ctx->states, total * sizeof(uint16_t))) != NC_OK) return rc;
+        if (moves && (rc = dev_reserve(ctx, ctx->moves, total)) != NC_OK) return rc;
+        // Big batches in PINNED memory: the kernels start at once and the event arrays follow on a third stream in
+        // chunks.  From pageable memory cudaMemcpyAsync is staged and blocks the host, so nothing would overlap
+        // (and the chunking would only add small copies): such calls take the plain copy path.
+        stream_in = total >= ctx->stream_in_min_events;
+        if (stream_in)
+        {
+            cudaPointerAttributes at;
+            for (const float* p : { mean + base, stdv + base, start + base })
+                if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeHost) stream_in = false;
+            cudaGetLastError();
+        }
+    }
+    // from here on work is in flight: a failure synchronises the context's streams before it returns, so that the
+    // caller's buffers and the context's scratch are quiescent when the error is reported
+#define NC_CUDA_INFLIGHT(call)                                                                                        \
+    do {                                                                                                              \
+        cudaError_t _e = (call);                                                                                      \
+        if (_e != cudaSuccess)                                                                                        \
+        {                                                                                                             \
+            cudaStreamSynchronize(ctx->stream3); cudaStreamSynchronize(ctx->stream2); cudaStreamSynchronize(ctx->stream); \
+            cudaGetLastError();                                                                                       \
+            NC_FAIL(ctx, NC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__);      \
+        }                                                                                                             \
+    } while (0)
     cudaStream_t s = ctx->stream;
-    NC_CUDA(ctx, cudaMemcpyAsync(ctx->jobs.p, jobs.data(), n_jobs * sizeof(nc::DevJob), cudaMemcpyHostToDevice, s));
-    NC_CUDA(ctx, cudaMemcpyAsync(ctx->order.p, order.data(), n_jobs * sizeof(unsigned), cudaMemcpyHostToDevice, s));
-    NC_CUDA(ctx, cudaMemsetAsync(ctx->counter.p, 0, 2 * sizeof(unsigned), s));
+    NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), n_jobs * sizeof(nc::DevJob), cudaMemcpyHostToDevice, s));
+    NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->order.p, order.data(), n_jobs * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+    NC_CUDA_INFLIGHT(cudaMemsetAsync(ctx->counter.p, 0, 2 * sizeof(unsigned), s));
 
     nc::VitArgs a;
     a.jobs = (const nc::DevJob*)ctx->jobs.p;
@@ -345,31 +387,23 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     a.colalloc = nullptr;
     a.stats = ctx->d_stats;
 
-    const uint64_t base = ev_off[0];
-    bool stream_in = false;
     a.landed = nullptr;
     a.ev_total = total;
     if (mem == NC_MEM_HOST)
     {
         const float* lsp = log_stdv ? log_stdv + base : nullptr;  // NULL: the kernel derives it (nc_logf)
-        if ((rc = dev_reserve(ctx, ctx->mean, total * sizeof(float))) != NC_OK) return rc;
-        if ((rc = dev_reserve(ctx, ctx->stdv, total * sizeof(float))) != NC_OK) return rc;
-        if ((rc = dev_reserve(ctx, ctx->start, total * sizeof(float))) != NC_OK) return rc;
-        if (lsp && (rc = dev_reserve(ctx, ctx->lstd, total * sizeof(float))) != NC_OK) return rc;
-        // Big batches: the kernels start at once and the event arrays follow on a third stream in chunks; a job
-        // waits (wait_events_landed) until the copy engine has delivered its events.  Small ones: plain copies.
-        stream_in = total >= ctx->stream_in_min_events;
+        // streamed input: a job waits (wait_events_landed) until the copy engine has delivered its events
         if (stream_in)
         {
-            NC_CUDA(ctx, cudaMemsetAsync(ctx->d_landed, 0, sizeof(unsigned long long), s));
-            NC_CUDA(ctx, cudaEventRecord(ctx->ev3, s));
+            NC_CUDA_INFLIGHT(cudaMemsetAsync(ctx->d_landed, 0, sizeof(unsigned long long), s));
+            NC_CUDA_INFLIGHT(cudaEventRecord(ctx->ev3, s));
         }
         else
         {
-            NC_CUDA(ctx, cudaMemcpyAsync(ctx->mean.p, mean + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
-            NC_CUDA(ctx, cudaMemcpyAsync(ctx->stdv.p, stdv + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
-            NC_CUDA(ctx, cudaMemcpyAsync(ctx->start.p, start + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
-            if (lsp) NC_CUDA(ctx, cudaMemcpyAsync(ctx->lstd.p, lsp, total * sizeof(float), cudaMemcpyHostToDevice, s));
+            NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->mean.p, mean + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
+            NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->stdv.p, stdv + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
+            NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->start.p, start + base, total * sizeof(float), cudaMemcpyHostToDevice, s));
+            if (lsp) NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->lstd.p, lsp, total * sizeof(float), cudaMemcpyHostToDevice, s));
         }
         if (stream_in) a.landed = ctx->d_landed;
         a.mean = (const float*)ctx->mean.p;
@@ -378,16 +412,8 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         a.log_stdv = lsp ? (const float*)ctx->lstd.p : nullptr;
         a.states = nullptr;
         a.moves = nullptr;
-        if (states || moves)
-        {
-            if ((rc = dev_reserve(ctx, ctx->states, total * sizeof(uint16_t))) != NC_OK) return rc;
-            a.states = (unsigned short*)ctx->states.p;
-        }
-        if (moves)
-        {
-            if ((rc = dev_reserve(ctx, ctx->moves, total)) != NC_OK) return rc;
-            a.moves = (unsigned char*)ctx->moves.p;
-        }
+        if (states || moves) a.states = (unsigned short*)ctx->states.p;
+        if (moves) a.moves = (unsigned char*)ctx->moves.p;
     }
     else
     {
@@ -406,7 +432,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         // launches are serialised (profilers, CUDA_LAUNCH_BLOCKING, pageable buffers): the data is then simply
         // there first.  Chunks are multiples of 32 events (whole 128-byte lines).
         cudaStream_t sc = ctx->stream3;
-        NC_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev3, 0));
+        NC_CUDA_INFLIGHT(cudaStreamWaitEvent(sc, ctx->ev3, 0));
         const float* lsp = log_stdv ? log_stdv + base : nullptr;
         uint64_t chunk = std::max< uint64_t >(ctx->stream_in_chunk, (total + nc_ctx::LANDED_SLOTS - 1) / nc_ctx::LANDED_SLOTS);
         chunk = (chunk + 31) & ~(uint64_t)31;
@@ -430,16 +456,16 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
             NC_FAIL(ctx, NC_ERR_CUDA, "nc_viterbi_packed: streamed event upload failed: %s", cudaGetErrorString(ce));
         }
     }
-    NC_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    NC_CUDA_INFLIGHT(cudaEventRecord(ctx->ev0, s));
     ctx->last_launches = 0;
     if (n_long)
     {
         // on the second stream, so it runs next to the alpha kernel (grid_b + fwd_a + tb_a <= number of SMs)
         cudaStream_t sb = n_short ? ctx->stream2 : s;
-        if (n_short) NC_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev0, 0));
+        if (n_short) NC_CUDA_INFLIGHT(cudaStreamWaitEvent(sb, ctx->ev0, 0));
         nc::viterbi_kernel<<< grid_b, nc::VIT_THREADS, nc::viterbi_smem_bytes(), sb >>>(a);
-        NC_CUDA(ctx, cudaGetLastError());
-        if (n_short) NC_CUDA(ctx, cudaEventRecord(ctx->ev2, sb));
+        NC_CUDA_INFLIGHT(cudaGetLastError());
+        if (n_short) NC_CUDA_INFLIGHT(cudaEventRecord(ctx->ev2, sb));
         ++ctx->last_launches;
     }
     if (n_short)
@@ -454,15 +480,11 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         b.n_tb = tb_a;
         if (want_path)
         {
-            // tickets | tail, head | release counter of every forward CTA (zeroed) | column allocator (one free extent)
-            const size_t tk_bytes = (size_t)n_short * sizeof(nc::TbTicket);
-            const size_t ctl_bytes = ((2 + 2 * (size_t)fwd_a) * sizeof(unsigned) + 15) & ~(size_t)15;
-            const size_t ca_bytes = nc::viterbi_alpha_colalloc_bytes();
-            if ((rc = dev_reserve(ctx, ctx->tb, tk_bytes + ctl_bytes + ca_bytes)) != NC_OK) return rc;
-            NC_CUDA(ctx, cudaMemsetAsync(ctx->tb.p, 0, tk_bytes + ctl_bytes, s));
+            // tickets, counters (zeroed) and the column allocator (one free extent)
+            NC_CUDA_INFLIGHT(cudaMemsetAsync(ctx->tb.p, 0, tk_bytes + ctl_bytes, s));
             ctx->colalloc_image.resize(ca_bytes);
             nc::viterbi_alpha_colalloc_init(ctx->colalloc_image.data(), (unsigned)(slab_a / a_col));
-            NC_CUDA(ctx, cudaMemcpyAsync((char*)ctx->tb.p + tk_bytes + ctl_bytes, ctx->colalloc_image.data(), ca_bytes, cudaMemcpyHostToDevice, s));
+            NC_CUDA_INFLIGHT(cudaMemcpyAsync((char*)ctx->tb.p + tk_bytes + ctl_bytes, ctx->colalloc_image.data(), ca_bytes, cudaMemcpyHostToDevice, s));
             b.tickets = (nc::TbTicket*)ctx->tb.p;
             b.tb_tail = (unsigned*)((char*)ctx->tb.p + tk_bytes);
             b.tb_head = b.tb_tail + 1;
@@ -470,22 +492,23 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
             b.colalloc = (char*)ctx->tb.p + tk_bytes + ctl_bytes;
         }
         nc::viterbi_alpha_kernel<<< fwd_a + tb_a, nc::VIT_THREADS, nc::viterbi_alpha_smem_bytes(), s >>>(b);
-        NC_CUDA(ctx, cudaGetLastError());
+        NC_CUDA_INFLIGHT(cudaGetLastError());
         ++ctx->last_launches;
-        if (n_long) NC_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev2, 0));
+        if (n_long) NC_CUDA_INFLIGHT(cudaStreamWaitEvent(s, ctx->ev2, 0));
     }
-    NC_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    NC_CUDA_INFLIGHT(cudaEventRecord(ctx->ev1, s));
 
-    NC_CUDA(ctx, cudaMemcpyAsync(path_logprob, ctx->path.p, n_jobs * sizeof(float), cudaMemcpyDeviceToHost, s));
+    NC_CUDA_INFLIGHT(cudaMemcpyAsync(path_logprob, ctx->path.p, n_jobs * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (mem == NC_MEM_HOST)
     {
-        if (states) NC_CUDA(ctx, cudaMemcpyAsync(states + base, ctx->states.p, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
-        if (moves) NC_CUDA(ctx, cudaMemcpyAsync(moves + base, ctx->moves.p, total, cudaMemcpyDeviceToHost, s));
+        if (states) NC_CUDA_INFLIGHT(cudaMemcpyAsync(states + base, ctx->states.p, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+        if (moves) NC_CUDA_INFLIGHT(cudaMemcpyAsync(moves + base, ctx->moves.p, total, cudaMemcpyDeviceToHost, s));
     }
-    NC_CUDA(ctx, cudaStreamSynchronize(s));
-    if (stream_in) NC_CUDA(ctx, cudaStreamSynchronize(ctx->stream3));
-    NC_CUDA(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
+    NC_CUDA_INFLIGHT(cudaStreamSynchronize(s));
+    if (stream_in) NC_CUDA_INFLIGHT(cudaStreamSynchronize(ctx->stream3));
+    NC_CUDA_INFLIGHT(cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
     return NC_OK;
+#undef NC_CUDA_INFLIGHT
 }
 
 int nc_viterbi_batch(nc_ctx* ctx, uint32_t n_jobs, const nc_vit_job* jobs, nc_vit_out* outs)

@@ -2,98 +2,53 @@
 // Parameter_Trainer (Parameter_Trainer.hpp:230-532) for batches of training sequences.
 //
 // Bit-exactness.  alpha, beta and log Pr[data] reproduce the reference bit for bit.  That needs
-//   * p7_FLogsum literally (logsum.hpp:141-154): max, min, the test `min == -inf || max-min >= 15.999f`,
-//     index (int)((max-min)*1000.f), the 16000-entry table built on the host in double (logsum.hpp:113-127);
+//   * p7_FLogsum literally (logsum.hpp:141-154) -- here in seven instructions with the same bits (nc_fwbw_core.cuh);
 //   * the reference's accumulation ORDER: from -inf, over the ascending merged predecessor list from_v(j)
 //     (forward) / successor list to_v(j) (backward), each edge with its exact weight.
-// The lists are never materialised.  Predecessors of j sorted by index fall into 16 "slots" (index >> 8):
-// slot s holds the two-step predecessor (s<<8)|(j>>4), the one-step predecessor (b<<10)|(j>>2) when
-// s == 4b + (j>>10), and j itself when s == j>>8; inside a slot the order is that of the low bytes.
-// Successors of j are two contiguous blocks, [(j&255)<<4, +16) and [(j&1023)<<2, +4), plus j.  An index that
-// occurs twice is ONE edge in the reference (std::set union, State_Transitions.hpp:205-209) whose weight
-// carries every matching overlap term; here the lower-class duplicate is replaced by -inf, and
-// p7_FLogsum(x, -inf) == x exactly, so the chain is the reference's chain.
+// The lists are never materialised; the per-thread column code (shared chain prefixes, merged duplicate edges) lives
+// in nc_fwbw_core.cuh as __host__ __device__ functions and is checked against the oracle on the host as well
+// (tests/test_fwbw_emu.py).
 //
 // Kernels (one wave = the sequences whose E/alpha/beta slabs fit the scratch pool):
 //   emission_kernel   E[i][j] = log_pr_corrected_emission(j, e_i) for every sequence (grid: seq x event tiles)
-//   fwbw_kernel       one CTA per sequence: forward, backward, log Pr[data]; alpha/beta to the slabs
-//   pm_stats_kernel   per event the six posterior-weighted sums of train_pm_params (:263-296)
+//   fwbw_kernel       one CTA per sequence: forward, log Pr[data], backward; alpha/beta to the slabs
+//   pm_stats_kernel   per event the six posterior-weighted sums of train_pm_params (:263-296), each the reference's
+//                     serial j = 0..4095 loop, 96 of them (16 events x 6 sums) in the lanes of three warps
 //   st_stats_kernel   one CTA per (group, strand): the three log-space accumulators of train_st_params (:471-514),
-//                     folded sequentially in the reference's (sequence, event, k-mer) order
-// The 3x3 solve, the clamps and exp() of the final ratios run on the host in nc_train.cpp.
+//                     folded in the reference's (sequence, event, k-mer) order, 32 terms per step (speculate the table
+//                     indices from the running value, verify, repeat: exactly the sequential result)
+// The 3x3 solve, the clamps and exp() of the final ratios run on the host in nc_train.cu.
 #include "nc_device.cuh"
+#include "nc_fwbw_core.cuh"
 #include "nc_kernels.h"
 
 namespace nc {
 
 namespace {
 
-constexpr int FB_THREADS = 512;
-constexpr int FB_SPT = 8;
-constexpr int COL_PAD_SHIFT = 4;  // phys(n) = n + 4 * (n >> 4): conflict-free 16-float block reads
-constexpr int COL_FLOATS = NC_N_STATES + 4 * (NC_N_STATES >> COL_PAD_SHIFT);  // 5120
+using fb::cphys;
+using fb::flogsum;
 
-__device__ __forceinline__ int cphys(int n) { return n + ((n >> COL_PAD_SHIFT) << 2); }
-
-// p7_FLogsum (logsum.hpp:141-154): max + tbl[(int)((max - min) * 1000.f)], or max when min == -inf or
-// max - min >= 15.999f.  Same bits with 9 instructions instead of 14 (the kernels are bound by the ALU pipe, where
-// FSETP/FSEL/SEL run at half rate):
-//   * max - min == |a - b| exactly (rounding is symmetric), used as an operand modifier: no min is formed;
-//   * min == -inf implies |a - b| == +inf >= 15.999f, so that test is subsumed; when both are -inf the
-//     difference is NaN, the comparison is false and -inf + tbl[.] == -inf == max;
-//   * the index is clamped through fminf(|a - b|, 15.999f) (15.999f * 1000.f == 15999.f): in range without a select,
-//     and only changed where the result is discarded.
-// NaN inputs (which the reference only meets on invalid events) are not reproduced.
-__device__ __forceinline__ float flogsum(float a, float b, const float* __restrict__ tbl)
-{
-    const float d = fabsf(__fsub_rn(a, b));
-    const float mx = fmaxf(a, b);
-    const int idx = __float2int_rz(__fmul_rn(fminf(d, 15.999f), 1000.0f));
-    const float r = __fadd_rn(mx, tbl[idx]);
-    return (d >= 15.999f) ? mx : r;
-}
-
-// Six sequential float sums at once: acc_s = sum over j = 0..4095 of T[s][j], s = 0..5, each the serial loop
-// `for j: acc += T[s][j]` itself -- lane s < 6 of one warp carries chain s, the terms stream from shared memory as
-// float4 one group ahead of the additions.  No screening: on training data most terms are live anyway (posteriors
-// are broad while the scaling is still off; measured ~3000 of 4096), and the chain of 4096 dependent FADDs
-// (~16 k cycles) is then the whole cost -- 5.6 k warp-instructions per event instead of ~70 k for six warps that
-// screen and compact (profiles/r1_training_kernels.md).  Rows are PM_ROW = 4096 + 4 floats apart so the six lanes'
-// float4 loads hit different banks.
+constexpr int FB_THREADS = fb::THREADS;
+constexpr int FB_SPT = fb::SPT;
+constexpr int COL_FLOATS = fb::COL_FLOATS;
 constexpr int FOLD_LIST = 80;
-constexpr int ST_CHUNK = FB_THREADS - 3 * 32;   // 416 k-mers per chunk of st_stats_kernel
-constexpr int PM_ROW = NC_N_STATES + 4;
-__device__ __forceinline__ float fold_six_sums_in_order(const float* __restrict__ T, const int lane)
-{
-    const float* R = T + (lane < 6 ? lane : 0) * PM_ROW;   // lanes >= 6 shadow chain 0
-    float acc = 0.0f;
-    float4 v = *reinterpret_cast< const float4* >(R);
-#pragma unroll 4
-    for (int j = 0; j < (int)NC_N_STATES; j += 4)
-    {
-        const float4 nv = *reinterpret_cast< const float4* >(R + j + 4);   // the last one reads the row's padding
-        acc = __fadd_rn(acc, v.x);
-        acc = __fadd_rn(acc, v.y);
-        acc = __fadd_rn(acc, v.z);
-        acc = __fadd_rn(acc, v.w);
-        v = nv;
-    }
-    return acc;
-}
+constexpr unsigned FULL = 0xffffffffu;
 
-// The log-space twin: acc = p7_FLogsum(acc, x_k) over k = 0..n-1 in order, n a multiple of 32, x_k = get(k).
+// acc = p7_FLogsum(acc, x_k) over k = 0..n-1 in order, n a multiple of 32, x_k = get(k).
 // A term with x == -inf or acc - x >= 15.999 returns acc unchanged now and for every larger acc (the running value
 // never decreases), so it is screened out; the survivors are folded from the per-warp list, padded with -inf.
-template < typename Get >
+// (log Pr[data]: one call per sequence; the trainer's long chains use fold32 below.)
+template < typename Get, typename TB >
 __device__ __forceinline__ float fold_logsum_in_order(float acc, const int n, Get get, float* __restrict__ lst,
-                                                      const float* __restrict__ tbl, const int lane)
+                                                      const TB& tbl, const int lane)
 {
     const unsigned lt = (1u << lane) - 1u;
     for (int base = 0; base < n; base += 32)
     {
         const float x = get(base + lane);
         const bool live = !((x == NC_NEG_INF) || (acc > x && __fsub_rn(acc, x) >= 15.999f));
-        const unsigned m = __ballot_sync(0xffffffffu, live);
+        const unsigned m = __ballot_sync(FULL, live);
         if (m == 0) continue;
         const int cnt = __popc(m);
         if (live) lst[__popc(m & lt)] = x;
@@ -110,20 +65,75 @@ __device__ __forceinline__ float fold_logsum_in_order(float acc, const int n, Ge
     return acc;
 }
 
-struct StSmem
+// One step of a long in-order p7_FLogsum chain: acc (warp-uniform) absorbs the 32 terms x (one per lane, lane order).
+// While acc >= x the step is acc' = acc + tbl[idx(acc - x)]: the lanes look their increments up with the value the
+// chain had at the START of the block, every lane then forms its own running value a_k = acc + t_0 + ... + t_{k-1}
+// (sequential float adds over the live lanes only, all lanes in lock step), and recomputes its index from a_k.  When
+// every index is confirmed the a_k are by induction the sequential chain's values and lane 31's a + t is the result;
+// otherwise the recomputed indices are the next guess (the first unconfirmed lane is certainly right then).  After
+// three rounds, or when a term exceeds the running value (start of a chain), the block is folded sequentially.
+template < typename TB >
+__device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl, const int lane)
 {
-    float term[2][3][ST_CHUNK];   // two buffers: computed by warps 3..15, folded by warps 0..2
-    float lst[3][FOLD_LIST];
-};
+    const bool live = !((x == NC_NEG_INF) || (acc > x && __fsub_rn(acc, x) >= 15.999f));
+    const unsigned m = __ballot_sync(FULL, live);
+    if (m == 0) return acc;
+    const bool spec_ok = __all_sync(FULL, !live || acc >= x);   // (false for acc == -inf with a finite term, and for NaN)
+    if (spec_ok)
+    {
+        const float INF = __int_as_float(0x7f800000);   // dead lanes: d = +inf selects the zero entry
+        unsigned e = tbl.addr(live ? __fsub_rn(acc, x) : INF);
+#pragma unroll 1
+        for (int round = 0; round < 3; ++round)
+        {
+            const float t = tbl.load(e);
+            float a = acc;
+            for (unsigned mm = m; mm; mm &= mm - 1)
+            {
+                const int k = __ffs(mm) - 1;
+                const float tk = __shfl_sync(FULL, t, k);
+                a = (k < lane) ? __fadd_rn(a, tk) : a;
+            }
+            const unsigned e2 = tbl.addr(live ? __fsub_rn(a, x) : INF);
+            const bool ok = !live || (a >= x && e2 == e);
+            if (__all_sync(FULL, ok)) return __shfl_sync(FULL, __fadd_rn(a, t), 31);
+            e = e2;
+        }
+    }
+    for (unsigned mm = m; mm; mm &= mm - 1)
+    {
+        const int k = __ffs(mm) - 1;
+        acc = flogsum(acc, __shfl_sync(FULL, x, k), tbl);
+    }
+    return acc;
+}
 
 struct FbSmem
 {
-    float tbl[16000];
+    float tbl[fb::TBL_N];
     float col[2][COL_FLOATS];
-    float red[FB_THREADS / 32];
+    float lut[64];
     float lst[FOLD_LIST];
     unsigned item;
 };
+
+constexpr int ST_CHUNK = FB_THREADS - 3 * 32;   // 416 terms per chunk of st_stats_kernel (13 producer warps)
+struct StSmem
+{
+    float tbl[fb::TBL_N];
+    float term[2][3][ST_CHUNK];   // two buffers: computed by warps 3..15, folded by warps 0..2
+    unsigned seq_id[NC_MAX_TRAIN_SEQS];      // the strand's sequences with >= 2 events, in order
+    unsigned seq_first[NC_MAX_TRAIN_SEQS + 1];  // first flattened (event) index of each
+    unsigned n_seq;
+};
+
+constexpr int PM_EV = 16;                 // events per CTA of pm_stats_kernel (= FB_EV_TILE)
+constexpr int PM_CHAINS = PM_EV * 6;      // 96 serial sums = the lanes of three warps
+constexpr int PM_ROW = PM_CHAINS + 1;     // row stride of the term buffer: producer lanes (consecutive states) hit different banks
+constexpr int PM_JT = 52;                 // states per tile: 13 producer warps x 32 = 8 event-pairs x 52 states
+constexpr int PM_TILES = (NC_N_STATES + PM_JT - 1) / PM_JT;   // 79
+static_assert(FB_EV_TILE == PM_EV, "pm_stats grid uses FB_EV_TILE");
+static_assert((FB_THREADS - 96) == 8 * PM_JT, "13 producer warps = 8 x PM_JT");
 
 } // namespace
 
@@ -183,8 +193,8 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
     FbSmem& sm = *reinterpret_cast< FbSmem* >(smem_raw);
     const int t = threadIdx.x;
     const int lane = t & 31;
-    for (int q = t; q < 16000; q += FB_THREADS) sm.tbl[q] = a.logsum_tbl[q];
-    const float* tbl = sm.tbl;
+    for (int q = t; q < fb::TBL_N; q += FB_THREADS) sm.tbl[q] = a.logsum_tbl[q];   // entry 15999 is 0 (nc_train.cu)
+    const fb::TblSmem tbl = fb::make_tbl_smem(sm.tbl);
 
     for (;;)
     {
@@ -199,28 +209,27 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
         const float* E = a.scratch + Q.slab;
         float* AL = a.scratch + Q.slab + 1 * (size_t)n * NC_N_STATES;
         float* BE = a.scratch + Q.slab + 2 * (size_t)n * NC_N_STATES;
+        if (t < 64) sm.lut[t] = J.lut[t];
+        __syncthreads();
 
-        // =========================== forward (Forward_Backward.hpp:58-89); thread owns j = 8t .. 8t+7
+        // =========================== forward (Forward_Backward.hpp:58-89); logical thread u owns j = 8u .. 8u+7
         {
-            const unsigned j0 = FB_SPT * t;
-            const unsigned g = t >> 1;
-            const float wT = J.lut[trans_mask(g, j0) & 0x3cu];
-            float wO[2];
-            wO[0] = J.lut[trans_mask(2 * t, j0) & 0x3eu];
-            wO[1] = J.lut[trans_mask(2 * t + 1, j0 + 4) & 0x3eu];
-            const int c = t >> 7;        // one-step predecessors sit in slots s with (s & 3) == c   (warp-uniform)
-            const int sS = t >> 5;       // j >> 8: slot of the self predecessor                       (warp-uniform)
-            const int kT = t >> 1;       // low byte of the two-step predecessors
+            fb::FwdConst C;
+            fb::fwd_const_init(C, fb::fwd_logical_thread(t), sm.lut);
+            const unsigned j0 = FB_SPT * (unsigned)C.u;
+            const int p0 = cphys((int)j0), p1 = cphys((int)j0 + 4);
+            float own[8];
             // column 0
             {
                 const float4 e0 = *reinterpret_cast< const float4* >(E + j0);
                 const float4 e1 = *reinterpret_cast< const float4* >(E + j0 + 4);
-                float4 a0 = make_float4(__fsub_rn(e0.x, a.log_n_states), __fsub_rn(e0.y, a.log_n_states),
-                                        __fsub_rn(e0.z, a.log_n_states), __fsub_rn(e0.w, a.log_n_states));
-                float4 a1 = make_float4(__fsub_rn(e1.x, a.log_n_states), __fsub_rn(e1.y, a.log_n_states),
-                                        __fsub_rn(e1.z, a.log_n_states), __fsub_rn(e1.w, a.log_n_states));
-                *reinterpret_cast< float4* >(sm.col[0] + cphys(j0)) = a0;
-                *reinterpret_cast< float4* >(sm.col[0] + cphys(j0 + 4)) = a1;
+                own[0] = __fsub_rn(e0.x, a.log_n_states); own[1] = __fsub_rn(e0.y, a.log_n_states);
+                own[2] = __fsub_rn(e0.z, a.log_n_states); own[3] = __fsub_rn(e0.w, a.log_n_states);
+                own[4] = __fsub_rn(e1.x, a.log_n_states); own[5] = __fsub_rn(e1.y, a.log_n_states);
+                own[6] = __fsub_rn(e1.z, a.log_n_states); own[7] = __fsub_rn(e1.w, a.log_n_states);
+                const float4 a0 = make_float4(own[0], own[1], own[2], own[3]), a1 = make_float4(own[4], own[5], own[6], own[7]);
+                *reinterpret_cast< float4* >(sm.col[0] + p0) = a0;
+                *reinterpret_cast< float4* >(sm.col[0] + p1) = a1;
                 *reinterpret_cast< float4* >(AL + j0) = a0;
                 *reinterpret_cast< float4* >(AL + j0 + 4) = a1;
             }
@@ -228,79 +237,22 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
             int cur = 0;
             for (unsigned i = 1; i < n; ++i)
             {
-                const float* A = sm.col[cur];
-                float vT[16];
-#pragma unroll
-                for (int s = 0; s < 16; ++s) vT[s] = __fadd_rn(wT, A[cphys((s << 8) | (int)g)]);
-                float vO[2][4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                {
-                    const float2 o = *reinterpret_cast< const float2* >(A + cphys((b << 10) + 2 * t));
-                    vO[0][b] = __fadd_rn(wO[0], o.x);
-                    vO[1][b] = __fadd_rn(wO[1], o.y);
-                }
+                const float* Ei = E + (size_t)i * NC_N_STATES + j0;
+                const float4 e0 = __ldg(reinterpret_cast< const float4* >(Ei));
+                const float4 e1 = __ldg(reinterpret_cast< const float4* >(Ei + 4));
+                const float e[8] = { e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w };
+                fb::fwd_column(C, sm.col[cur], tbl, e, own);
+                const float4 a0 = make_float4(own[0], own[1], own[2], own[3]), a1 = make_float4(own[4], own[5], own[6], own[7]);
                 float* An = sm.col[cur ^ 1];
-                const float* Ei = E + (size_t)i * NC_N_STATES;
-                // one state at a time (NOT unrolled): with the 16 slots unrolled inside, an unrolled k loop makes
-                // the kernel 290 KB of SASS and every column refetches it through the instruction cache
-                // (stall_no_instruction was 5 cycles per issue).  The other warps of the two resident CTAs hide
-                // the latency of the now sequential chains.
-#pragma unroll 1
-                for (int k = 0; k < FB_SPT; ++k)
-                {
-                    const int hh = k >> 2;
-                    const unsigned j = j0 + k;
-                    const float own_k = A[cphys(j)];
-                    const float e_k = __ldg(Ei + j);
-                    const int kO = (2 * t + hh) & 255;
-                    const int kS = j & 255;
-                    const bool oBefT = kO < kT, oEqT = kO == kT;
-                    const bool sEqT = kS == kT, sEqO = kS == kO;
-                    const float vS = __fadd_rn(J.lut[trans_mask(j, j)], own_k);
-                    float acc = NC_NEG_INF;
-#pragma unroll
-                    for (int s = 0; s < 16; ++s)
-                    {
-                        const bool hasO = (s & 3) == c;
-                        const bool hasS = s == sS;
-                        if (!hasO && !hasS) acc = flogsum(acc, vT[s], tbl);
-                        else
-                        {
-                            const bool dropT = (hasO && oEqT) || (hasS && sEqT);
-                            const bool dropO = !hasO || (hasS && sEqO);
-                            const float xT = dropT ? NC_NEG_INF : vT[s];
-                            const float xO = dropO ? NC_NEG_INF : (hh ? vO[1][s >> 2] : vO[0][s >> 2]);
-                            const bool oFirst = hasO && oBefT;
-                            const float first = oFirst ? xO : xT;
-                            const float second = oFirst ? xT : xO;
-                            if (!hasS)
-                            {
-                                acc = flogsum(acc, first, tbl);
-                                acc = flogsum(acc, second, tbl);
-                            }
-                            else
-                            {
-                                const int pos = (kT < kS ? 1 : 0) + ((hasO && kO < kS) ? 1 : 0);
-                                acc = flogsum(acc, pos == 0 ? vS : NC_NEG_INF, tbl);
-                                acc = flogsum(acc, first, tbl);
-                                acc = flogsum(acc, pos == 1 ? vS : NC_NEG_INF, tbl);
-                                acc = flogsum(acc, second, tbl);
-                                acc = flogsum(acc, pos == 2 ? vS : NC_NEG_INF, tbl);
-                            }
-                        }
-                    }
-                    An[cphys(j)] = __fadd_rn(e_k, acc);
-                }
-                // the thread's 8 new values, read back as two float4, go to the slab with vector stores
-                *reinterpret_cast< float4* >(AL + (size_t)i * NC_N_STATES + j0) = *reinterpret_cast< const float4* >(An + cphys(j0));
-                *reinterpret_cast< float4* >(AL + (size_t)i * NC_N_STATES + j0 + 4) = *reinterpret_cast< const float4* >(An + cphys(j0 + 4));
+                *reinterpret_cast< float4* >(An + p0) = a0;
+                *reinterpret_cast< float4* >(An + p1) = a1;
+                float* Ao = AL + (size_t)i * NC_N_STATES + j0;
+                *reinterpret_cast< float4* >(Ao) = a0;
+                *reinterpret_cast< float4* >(Ao + 4) = a1;
                 cur ^= 1;
                 __syncthreads();
             }
-            // log Pr[data]: sequential fold of the last column, ascending j (Forward_Backward.hpp:129-134).
-            // One warp: each lane screens 32 values against the running sum -- a term with sum - x >= 15.999
-            // leaves p7_FLogsum's result unchanged now and for every larger sum -- and only the rest is folded.
+            // log Pr[data]: sequential fold of the last column, ascending j (Forward_Backward.hpp:129-134), one warp
             if (t < 32)
             {
                 const float* A = sm.col[cur];
@@ -312,118 +264,31 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
 
         // =========================== backward (Forward_Backward.hpp:93-125); thread owns j = t + 512k
         {
-            const int tb = (t & 255) << 4;                 // two-step successors tb .. tb+15 (same for all 8 states)
-            const float wTb = J.lut[trans_mask(t, tb) & 0x3cu];
-            float wOb[2];
-            int ob[2];
-            ob[0] = t << 2;                                // one-step successors of j with (j & 1023) == t
-            ob[1] = (t + 512) << 2;                        //                                      == t + 512
-            wOb[0] = J.lut[trans_mask(t, ob[0]) & 0x3eu];
-            wOb[1] = J.lut[trans_mask(t + 512, ob[1]) & 0x3eu];
-            // beta[n-1] = 0
-            {
+            fb::BwdConst C;
+            fb::bwd_const_init(C, t, sm.lut);
 #pragma unroll
-                for (int k = 0; k < FB_SPT; ++k)
-                {
-                    const int j = t + FB_THREADS * k;
-                    sm.col[0][cphys(j)] = 0.0f;
-                    BE[(size_t)(n - 1) * NC_N_STATES + j] = 0.0f;
-                }
+            for (int k = 0; k < FB_SPT; ++k)
+            {
+                const unsigned code = fb::bwd_lane_code(t, k);
+                const unsigned c0 = __shfl_sync(FULL, code, 0);
+                if (__all_sync(FULL, code == c0)) C.paths |= c0 << (2 * k);
+            }
+            // beta[n-1] = 0
+#pragma unroll
+            for (int k = 0; k < FB_SPT; ++k)
+            {
+                const int j = t + FB_THREADS * k;
+                sm.col[0][cphys(j)] = 0.0f;
+                BE[(size_t)(n - 1) * NC_N_STATES + j] = 0.0f;
             }
             __syncthreads();
             int cur = 0;
             for (unsigned ip1 = n - 1; ip1 > 0; --ip1)
             {
-                const unsigned i = ip1 - 1;
-                const float* Bn = sm.col[cur];
-                const float* En = E + (size_t)ip1 * NC_N_STATES;
-                float vT[16];
-#pragma unroll
-                for (int v = 0; v < 4; ++v)
-                {
-                    const float4 e = __ldg(reinterpret_cast< const float4* >(En + tb) + v);
-                    const float4 b = *reinterpret_cast< const float4* >(Bn + cphys(tb) + 4 * v);
-                    vT[4 * v + 0] = __fadd_rn(__fadd_rn(wTb, e.x), b.x);
-                    vT[4 * v + 1] = __fadd_rn(__fadd_rn(wTb, e.y), b.y);
-                    vT[4 * v + 2] = __fadd_rn(__fadd_rn(wTb, e.z), b.z);
-                    vT[4 * v + 3] = __fadd_rn(__fadd_rn(wTb, e.w), b.w);
-                }
                 float* Bc = sm.col[cur ^ 1];
-#pragma unroll
-                for (int f = 0; f < 2; ++f)
-                {
-                    float vO[4];
-                    {
-                        const float4 e = __ldg(reinterpret_cast< const float4* >(En + ob[f]));
-                        const float4 b = *reinterpret_cast< const float4* >(Bn + cphys(ob[f]));
-                        vO[0] = __fadd_rn(__fadd_rn(wOb[f], e.x), b.x);
-                        vO[1] = __fadd_rn(__fadd_rn(wOb[f], e.y), b.y);
-                        vO[2] = __fadd_rn(__fadd_rn(wOb[f], e.z), b.z);
-                        vO[3] = __fadd_rn(__fadd_rn(wOb[f], e.w), b.w);
-                    }
-                    // merged, ordered list of the 20 block successors of this family
-                    const bool oIn = (ob[f] >> 4) == (tb >> 4);
-                    const bool oBef = !oIn && ob[f] < tb;
-                    const int c4 = (ob[f] & 15) >> 2;
-                    float L[20];
-#pragma unroll
-                    for (int q = 0; q < 20; ++q)
-                    {
-                        // position q holds: oBef ? (q < 4 ? O[q] : T[q-4]) : (q < 16 ? T[q] : O[q-16])
-                        float asT, asO;
-                        if (q < 4) { asO = vO[q]; asT = vT[q]; }
-                        else if (q < 16) { asO = vT[q - 4]; asT = vT[q]; }
-                        else { asO = vT[q - 4]; asT = vO[q - 16]; }
-                        float val = oBef ? asO : asT;
-                        if (q < 16)
-                        {
-                            // oIn: the block is T with entries 4*c4 .. 4*c4+3 carrying the one-step weight
-                            const bool rep = oIn && ((q >> 2) == c4);
-                            val = rep ? vO[q & 3] : val;
-                        }
-                        else val = oIn ? NC_NEG_INF : val;
-                        L[q] = val;
-                    }
-#pragma unroll 1
-                    for (int kk = 0; kk < 4; ++kk)
-                    {
-                        const int k = 2 * kk + f;
-                        const int j = t + FB_THREADS * k;
-                        const float vS = __fadd_rn(__fadd_rn(J.lut[trans_mask(j, j)], __ldg(En + j)), Bn[cphys(j)]);
-                        const bool sInT = (j >> 4) == (tb >> 4);
-                        const bool sInO = (j >> 2) == (ob[f] >> 2);
-                        // position of j inside the list when it coincides with a block entry, else -1
-                        int mpos = -1;
-                        if (sInT) mpos = (oBef ? 4 : 0) + (j & 15);
-                        else if (sInO) mpos = (oBef ? 0 : 16) + (j & 3);
-                        // otherwise: number of blocks entirely below j
-                        const int pos = (mpos >= 0) ? -1 : ((j > tb ? 1 : 0) + ((!oIn && j > ob[f]) ? 1 : 0));
-                        // p7_FLogsum(-inf, x) == x: the first fold is a select
-                        float acc = (pos == 0) ? vS : NC_NEG_INF;
-                        if (mpos < 0)
-                        {
-                            // common case: j is not one of its own block successors, the list is used as it is
-#pragma unroll
-                            for (int q = 0; q < 20; ++q)
-                            {
-                                if (q == 4) acc = flogsum(acc, (oBef && pos == 1) ? vS : NC_NEG_INF, tbl);
-                                if (q == 16) acc = flogsum(acc, (!oBef && pos == 1) ? vS : NC_NEG_INF, tbl);
-                                acc = flogsum(acc, L[q], tbl);
-                            }
-                        }
-                        else
-                        {
-#pragma unroll
-                            for (int q = 0; q < 20; ++q)
-                            {
-                                acc = flogsum(acc, (q == mpos) ? vS : L[q], tbl);   // (pos == -1: no fold between the blocks)
-                            }
-                        }
-                        acc = flogsum(acc, pos == 2 ? vS : NC_NEG_INF, tbl);
-                        Bc[cphys(j)] = acc;
-                        BE[(size_t)i * NC_N_STATES + j] = acc;
-                    }
-                }
+                float* Bo = BE + (size_t)(ip1 - 1) * NC_N_STATES;
+                fb::bwd_column(C, sm.col[cur], E + (size_t)ip1 * NC_N_STATES, sm.lut, tbl,
+                               [&](int j, float v) { Bc[cphys(j)] = v; Bo[j] = v; });
                 cur ^= 1;
                 __syncthreads();
             }
@@ -440,130 +305,156 @@ size_t st_stats_smem_bytes() { return sizeof(StSmem); }
 //   l0 = sum_j p*lambda,  l1 = sum_j p*lambda/eta,  l2 = sum_j p*lambda/eta^2      (UNSCALED model)
 // with p = exp(alpha + beta - logZ).  The 3x3 system built from these sums is ill-conditioned (level means are
 // 58 +- 6 pA), so the float rounding of the reference's SEQUENTIAL j = 0..4095 accumulation is visible in the trained
-// shift/scale/var at the 1e-4 level: the order is reproduced exactly.  All terms are >= 0, so the running sum never
-// shift/scale/var at the 1e-4 level: the order is reproduced exactly, by running the six serial loops themselves in six
-// lanes of one warp (fold_six_sums_in_order).
+// shift/scale/var at the 1e-4 level: every sum is the reference's serial loop itself.  A serial sum is a chain of 4096
+// dependent FADDs (4 cycles each), so one CTA runs 96 of them at once -- 16 events x 6 sums, one per lane of warps
+// 0..2 -- while warps 3..15 produce the terms of the next 52 states for all 16 events into the other half of a
+// double-buffered tile (row stride 97 floats: the producers' lanes are consecutive states, the folding lanes
+// consecutive sums; both conflict-free).
 __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* term = reinterpret_cast< float* >(smem_raw);  // [6][PM_ROW]
+    float* term = reinterpret_cast< float* >(smem_raw);  // [2][PM_JT][PM_ROW]
     const unsigned seq = blockIdx.y;
     const FbSeq& Q = a.seqs[seq];
-    const unsigned i0 = blockIdx.x * FB_EV_TILE;
+    const unsigned i0 = blockIdx.x * PM_EV;
     if (i0 >= Q.n_events) return;
     const unsigned n = Q.n_events;
     const DevJob& J = a.jobs[Q.job];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const unsigned j0 = FB_SPT * t;
+    const int t = threadIdx.x;
     const float* M = a.models + (size_t)J.model * MODEL_FLOATS;
     const float* AL = a.scratch + Q.slab + 1 * (size_t)n * NC_N_STATES;
     const float* BE = a.scratch + Q.slab + 2 * (size_t)n * NC_N_STATES;
     const float logz = a.log_pr_data[seq];
-    float mu[FB_SPT], sg2[FB_SPT], lam[FB_SPT], eta[FB_SPT];
-#pragma unroll
-    for (int k = 0; k < FB_SPT; ++k)
+    const unsigned n_ev = min((unsigned)PM_EV, n - i0);
+
+    if (t < PM_CHAINS)
     {
-        mu[k] = __ldg(M + 0 * NC_N_STATES + j0 + k);
-        const float sg = __ldg(M + 1 * NC_N_STATES + j0 + k);
-        sg2[k] = __fmul_rn(sg, sg);
-        eta[k] = __ldg(M + 2 * NC_N_STATES + j0 + k);
-        lam[k] = __ldg(M + 3 * NC_N_STATES + j0 + k);
+        // ---- folding lanes: chain c = 6 * event + sum
+        float acc = 0.0f;
+        for (int tile = 0; tile < PM_TILES; ++tile)
+        {
+            __syncthreads();   // tile `tile` is complete in buffer tile & 1
+            const float* T = term + (size_t)(tile & 1) * PM_JT * PM_ROW + t;
+            const int nj = min(PM_JT, (int)NC_N_STATES - tile * PM_JT);
+#pragma unroll 4
+            for (int jl = 0; jl < nj; ++jl) acc = __fadd_rn(acc, T[jl * PM_ROW]);
+        }
+        const unsigned ev = (unsigned)t / 6u, s = (unsigned)t % 6u;
+        if (ev < n_ev) a.pm_stats[(Q.ev_out + i0 + ev) * 6 + s] = acc;
     }
-    const unsigned i1 = min(i0 + FB_EV_TILE, n);
-    for (unsigned i = i0; i < i1; ++i)
+    else
     {
-        float al[FB_SPT], be[FB_SPT];
-        *reinterpret_cast< float4* >(al) = *reinterpret_cast< const float4* >(AL + (size_t)i * NC_N_STATES + j0);
-        *reinterpret_cast< float4* >(al + 4) = *reinterpret_cast< const float4* >(AL + (size_t)i * NC_N_STATES + j0 + 4);
-        *reinterpret_cast< float4* >(be) = *reinterpret_cast< const float4* >(BE + (size_t)i * NC_N_STATES + j0);
-        *reinterpret_cast< float4* >(be + 4) = *reinterpret_cast< const float4* >(BE + (size_t)i * NC_N_STATES + j0 + 4);
+        // ---- producers: thread p handles state jt*52 + (p % 52) for the events (p / 52) and (p / 52) + 8
+        const int p = t - PM_CHAINS;
+        const int jl = p % PM_JT, eg = p / PM_JT;   // eg = 0..7
+        for (int tile = 0; tile < PM_TILES; ++tile)
+        {
+            const int j = tile * PM_JT + jl;
+            float* T = term + (size_t)(tile & 1) * PM_JT * PM_ROW + jl * PM_ROW;
+            if (j < (int)NC_N_STATES)
+            {
+                const float mu = __ldg(M + 0 * NC_N_STATES + j);
+                const float sg = __ldg(M + 1 * NC_N_STATES + j);
+                const float sg2 = __fmul_rn(sg, sg);
+                const float eta = __ldg(M + 2 * NC_N_STATES + j);
+                const float lam = __ldg(M + 3 * NC_N_STATES + j);
 #pragma unroll
-        for (int k = 0; k < FB_SPT; ++k)
-        {
-            const float p = nc_expf(__fsub_rn(__fadd_rn(al[k], be[k]), logz));
-            const float ts0 = __fdiv_rn(p, sg2[k]);
-            const float ts1 = __fmul_rn(ts0, mu[k]);
-            const float tl0 = __fmul_rn(p, lam[k]);
-            const float tl1 = __fdiv_rn(tl0, eta[k]);
-            term[0 * PM_ROW + j0 + k] = ts0;
-            term[1 * PM_ROW + j0 + k] = ts1;
-            term[2 * PM_ROW + j0 + k] = __fmul_rn(ts1, mu[k]);
-            term[3 * PM_ROW + j0 + k] = tl0;
-            term[4 * PM_ROW + j0 + k] = tl1;
-            term[5 * PM_ROW + j0 + k] = __fdiv_rn(tl1, eta[k]);
+                for (int r = 0; r < 2; ++r)
+                {
+                    const unsigned ev = (unsigned)(eg + 8 * r);
+                    float ts0 = 0.f, ts1 = 0.f, ts2 = 0.f, tl0 = 0.f, tl1 = 0.f, tl2 = 0.f;
+                    if (ev < n_ev)
+                    {
+                        const size_t o = (size_t)(i0 + ev) * NC_N_STATES + j;
+                        const float pst = nc_expf(__fsub_rn(__fadd_rn(__ldcs(AL + o), __ldcs(BE + o)), logz));
+                        ts0 = __fdiv_rn(pst, sg2);
+                        ts1 = __fmul_rn(ts0, mu);
+                        ts2 = __fmul_rn(ts1, mu);
+                        tl0 = __fmul_rn(pst, lam);
+                        tl1 = __fdiv_rn(tl0, eta);
+                        tl2 = __fdiv_rn(tl1, eta);
+                    }
+                    float* R = T + 6 * ev;
+                    R[0] = ts0; R[1] = ts1; R[2] = ts2; R[3] = tl0; R[4] = tl1; R[5] = tl2;
+                }
+            }
+            __syncthreads();   // publishes tile `tile`; the folding lanes are at most one tile behind
         }
-        __syncthreads();
-        if (warp == 0)
-        {
-            const float acc = fold_six_sums_in_order(term, lane);
-            if (lane < 6) a.pm_stats[(Q.ev_out + i) * 6 + lane] = acc;
-        }
-        __syncthreads();
     }
 }
 
-size_t pm_stats_smem_bytes() { return 6 * PM_ROW * sizeof(float); }
+size_t pm_stats_smem_bytes() { return (size_t)2 * PM_JT * PM_ROW * sizeof(float); }
 
 // ------------------------------------------------------------------------------------------------
 // train_st_params' accumulators (Parameter_Trainer.hpp:434-517) for one (group, strand):
 //   denom (+)= post(i,j1);  stay (+)= min(joint(j1->j1 | log p_stay), post);
 //   skip (+)= log(exp(post) - exp(min(d01, post))),  d01 = stay' (+) the 4 one-step joints with log(p_step/4)
-// over the strand's sequences in order, events i < n-1, the 2160 training k-mers in ascending order.
-// Warps 3..15 compute the terms of 416 k-mers at a time into one of two buffers while warps 0..2 fold the previous
-// chunk sequentially, one accumulator each (screening out terms that cannot change the running value, as in the
-// logZ fold): the gathers and the expf/logf of chunk c+1 overlap the dependent p7_FLogsum chain of chunk c.
-__global__ void __launch_bounds__(FB_THREADS) st_stats_kernel(const FbArgs a)
+// over the strand's sequences in order, events i < n-1, the 2160 training k-mers in ascending order: ONE chain of
+// (events x 2160) terms per accumulator.  The chain is cut into chunks of 416 consecutive terms (chunks run across
+// event boundaries); warps 3..15 compute the terms of a chunk into one of two buffers while warps 0..2 fold the
+// previous chunk, one accumulator each, 32 terms per step (fold32).
+__global__ void __launch_bounds__(FB_THREADS, 3) st_stats_kernel(const FbArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StSmem& ss = *reinterpret_cast< StSmem* >(smem_raw);
-    // the p7_FLogsum table stays in global memory here: with 11 KB of shared memory per CTA four CTAs fit an SM
-    // (the kernel is latency-bound by its sequential folds) and the 64 KB table lives in the L1 the carve-out leaves
-    const float* __restrict__ tbl = a.logsum_tbl;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const unsigned grp = blockIdx.x;
     const unsigned st = blockIdx.y;
     const FbGroup& G = a.groups[grp];
+    for (int q = t; q < fb::TBL_N; q += FB_THREADS) ss.tbl[q] = a.logsum_tbl[q];
+    if (t == 0)
+    {
+        unsigned ns = 0, first = 0;
+        for (unsigned sq = G.seq_begin; sq < G.seq_end; ++sq)
+            if (a.seqs[sq].strand == st && a.seqs[sq].n_events >= 2)
+            {
+                ss.seq_id[ns] = sq;
+                ss.seq_first[ns] = first;
+                first += a.seqs[sq].n_events - 1;
+                ++ns;
+            }
+        ss.seq_first[ns] = first;
+        ss.n_seq = ns;
+    }
+    __syncthreads();
+    const fb::TblSmem tbl = fb::make_tbl_smem(ss.tbl);
+    const unsigned n_km = a.n_train_kmers;
+    const unsigned n_seq = ss.n_seq;
+    const unsigned long long n_items = (unsigned long long)ss.seq_first[n_seq] * n_km;
+    const unsigned n_chunks = (unsigned)((n_items + ST_CHUNK - 1) / ST_CHUNK);
     const float log_p_stay = G.log_p_stay[st];
     const float log_p_step_4 = G.log_p_step_4[st];
-    const unsigned n_km = a.n_train_kmers;
 
-    // the (sequence, event, chunk) items in the reference's order; every thread walks the same two cursors
-    struct Cursor { unsigned sq, i, base; };
-    auto skip = [&](Cursor& c) { while (c.sq < G.seq_end && (a.seqs[c.sq].strand != st || a.seqs[c.sq].n_events < 2)) ++c.sq; };
-    auto valid = [&](const Cursor& c) { return c.sq < G.seq_end; };
-    auto advance = [&](Cursor& c) {
-        c.base += ST_CHUNK;
-        if (c.base >= n_km)
-        {
-            c.base = 0;
-            if (++c.i + 1 >= a.seqs[c.sq].n_events) { c.i = 0; ++c.sq; skip(c); }
-        }
-    };
-    auto compute = [&](const Cursor& c, float (*term)[ST_CHUNK]) {
+    auto compute = [&](unsigned chunk, float (*term)[ST_CHUNK]) {
         const int ct = t - 3 * 32;   // 0..415
-        const FbSeq& Q = a.seqs[c.sq];
-        const unsigned n = Q.n_events;
-        const float* E = a.scratch + Q.slab;
-        const float* AL = a.scratch + Q.slab + 1 * (size_t)n * NC_N_STATES;
-        const float* BE = a.scratch + Q.slab + 2 * (size_t)n * NC_N_STATES;
-        const float logz = a.log_pr_data[c.sq];
-        const float* Ai = AL + (size_t)c.i * NC_N_STATES;
-        const float* Bi = BE + (size_t)c.i * NC_N_STATES;
-        const float* Bn = BE + (size_t)(c.i + 1) * NC_N_STATES;
-        const float* En = E + (size_t)(c.i + 1) * NC_N_STATES;
+        const unsigned long long item = (unsigned long long)chunk * ST_CHUNK + (unsigned)ct;
         float t_denom = NC_NEG_INF, t_stay = NC_NEG_INF, t_skip = NC_NEG_INF;
-        if (c.base + ct < n_km)
+        if (item < n_items)
         {
-            const unsigned j1 = a.train_kmers[c.base + ct];
-            const float al = Ai[j1];
-            const float log_p_j1 = __fsub_rn(__fadd_rn(al, Bi[j1]), logz);
+            const unsigned ef = (unsigned)(item / n_km), km = (unsigned)(item - (unsigned long long)ef * n_km);
+            unsigned s = 0;
+            while (s + 1 < n_seq && ef >= ss.seq_first[s + 1]) ++s;
+            const unsigned sq = ss.seq_id[s], i = ef - ss.seq_first[s];
+            const FbSeq& Q = a.seqs[sq];
+            const unsigned n = Q.n_events;
+            const float* E = a.scratch + Q.slab;
+            const float* AL = E + 1 * (size_t)n * NC_N_STATES;
+            const float* BE = E + 2 * (size_t)n * NC_N_STATES;
+            const float logz = a.log_pr_data[sq];
+            const float* Ai = AL + (size_t)i * NC_N_STATES;
+            const float* Bi = BE + (size_t)i * NC_N_STATES;
+            const float* Bn = BE + (size_t)(i + 1) * NC_N_STATES;
+            const float* En = E + (size_t)(i + 1) * NC_N_STATES;
+            const unsigned j1 = __ldg(a.train_kmers + km);
+            const unsigned nb = (j1 & 1023u) << 2;   // the four one-step successors are one aligned float4
+            const float al = __ldg(Ai + j1), bi = __ldg(Bi + j1), en = __ldg(En + j1), bn = __ldg(Bn + j1);
+            const float4 e4 = __ldg(reinterpret_cast< const float4* >(En + nb));
+            const float4 b4 = __ldg(reinterpret_cast< const float4* >(Bn + nb));
+            const float log_p_j1 = __fsub_rn(__fadd_rn(al, bi), logz);
             // joint(i, j1, j2, lt) = alpha + lt + emission(j2, e_{i+1}) + beta(i+1, j2) - logZ   (:457-469)
-            float jj = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_stay), En[j1]), Bn[j1]), logz);
+            float jj = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_stay), en), bn), logz);
             if (jj > log_p_j1) jj = log_p_j1;
             float s2 = flogsum(NC_NEG_INF, jj, tbl);
-            const unsigned nb = (j1 & 1023u) << 2;   // the four one-step successors are one aligned float4
-            const float4 e4 = *reinterpret_cast< const float4* >(En + nb);
-            const float4 b4 = *reinterpret_cast< const float4* >(Bn + nb);
             const float ev[4] = { e4.x, e4.y, e4.z, e4.w }, bv[4] = { b4.x, b4.y, b4.z, b4.w };
 #pragma unroll
             for (int b = 0; b < 4; ++b)
@@ -582,30 +473,29 @@ __global__ void __launch_bounds__(FB_THREADS) st_stats_kernel(const FbArgs a)
         term[2][ct] = t_skip;
     };
 
-    Cursor cc = { G.seq_begin, 0, 0 };
-    skip(cc);
-    if (valid(cc) && warp >= 3) compute(cc, ss.term[0]);
+    if (n_chunks && warp >= 3) compute(0, ss.term[0]);
     __syncthreads();
-    Cursor fc = cc;
-    advance(cc);
-    int buf = 0;
     float acc = NC_NEG_INF;   // warps 0..2: denom, stay, skip
-    while (valid(fc))
+    for (unsigned c = 0; c < n_chunks; ++c)
     {
+        const int buf = (int)(c & 1u);
         if (warp >= 3)
         {
-            if (valid(cc)) compute(cc, ss.term[buf ^ 1]);
+            if (c + 1 < n_chunks) compute(c + 1, ss.term[buf ^ 1]);
         }
         else
         {
-            // NaN terms (log of a negative difference cannot occur: d01 <= post) are folded like the reference would
             const float* Tw = ss.term[buf][warp];
-            acc = fold_logsum_in_order(acc, ST_CHUNK, [&](int k) { return Tw[k]; }, ss.lst[warp], tbl, lane);
+            float x = Tw[lane];
+#pragma unroll 1
+            for (int base = 0; base < ST_CHUNK; base += 32)
+            {
+                const float xn = (base + 32 < ST_CHUNK) ? Tw[base + 32 + lane] : NC_NEG_INF;
+                acc = fold32(acc, x, tbl, lane);
+                x = xn;
+            }
         }
         __syncthreads();
-        fc = cc;
-        advance(cc);
-        buf ^= 1;
     }
     if (warp < 3 && lane == 0) a.st_stats[(grp * 2 + st) * 3 + warp] = acc;   // denom, stay, skip
 }

@@ -24,13 +24,18 @@ unsigned max_self_overlap(unsigned i)
 
 int ensure_train_tables(nc_ctx* ctx)
 {
-    if (ctx->d_logsum_tbl && ctx->d_train_kmers) return NC_OK;
+    // every entry point that touches the device selects the context's GPU first: the caller's thread may have
+    // another one current (several contexts driven from one thread, or a host framework that switched devices)
     NC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->d_logsum_tbl && ctx->d_train_kmers) return NC_OK;
     if (!ctx->d_logsum_tbl)
     {
-        // p7_FLogsumInit (logsum.hpp:113-127): double log/exp, stored as float
+        // p7_FLogsumInit (logsum.hpp:113-127): double log/exp, stored as float.  Entry 15999 is set to 0: the reference
+        // never reads it (its index is reached exactly when max - min >= 15.999f, where p7_FLogsum returns max), and the
+        // kernels' p7_FLogsum relies on it to return max + 0 there without a compare (nc_fwbw_core.cuh)
         std::vector< float > tbl(16000);
         for (int i = 0; i < 16000; ++i) tbl[i] = (float)std::log(1. + std::exp((double)-i / 1000.f));
+        tbl[15999] = 0.0f;
         NC_CUDA(ctx, cudaMalloc(&ctx->d_logsum_tbl, tbl.size() * sizeof(float)));
         NC_CUDA(ctx, cudaMemcpy(ctx->d_logsum_tbl, tbl.data(), tbl.size() * sizeof(float), cudaMemcpyHostToDevice));
     }

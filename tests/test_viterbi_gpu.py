@@ -248,6 +248,15 @@ def test_streamed_event_upload(port, models, vit_mode, monkeypatch):
         c.set_viterbi_mode(L.NC_VIT_BACKPOINTER if vit_mode == "backpointer" else L.NC_VIT_AUTO)
         mid = c.register_model(table, 0)
         batch = synth.make_batch(53, table, [5000, 33, 1200, 7000, 250, 4097, 640] * 3)
+        # the streamed path needs PINNED host memory (pageable calls take the plain copy path)
+        import torch
+        keep = {k: torch.from_numpy(batch[k]).pin_memory() for k in ("mean", "stdv", "start")}
+        for k, v in keep.items():
+            batch[k] = v.numpy()
+        _check_batch(c, port, table, mid, batch, None, None)
+        # and the same call from pageable memory (plain copies): same bits
+        for k in keep:
+            batch[k] = batch[k].copy()
         _check_batch(c, port, table, mid, batch, None, None)
     finally:
         c.close()
