@@ -162,6 +162,11 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
                          const float* mean, const float* stdv, const float* start,
                          const nc_train_in* in, const nc_train_opts* opts, nc_train_out* out);
 
+/* Device time of the training kernels since the last reset (CUDA events on the context's stream, summed over the waves
+ * of every nc_train_round_batch / nc_fwbw call): out8 = { emission_kernel ms, fwbw_kernel ms, pm_stats_kernel ms,
+ * st_stats_kernel ms, Forward/Backward events processed, kernels launched, waves, 0 }. */
+int nc_ctx_train_stats(nc_ctx* ctx, double* out8, int reset);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-side helpers that restate small pieces of reference arithmetic needed around the calls. */
 /* alg::mean_stdv_of<float> (hpptools alg.hpp:466-482) */

@@ -91,6 +91,13 @@ class Context:
         keys = ("fwd_cycles", "fwd_wait_slab_cycles", "tb_busy_cycles", "tb_wait_cycles", "tb_passes", "tb_lane_steps", "tb_jobs")
         return {k: int(v) for k, v in zip(keys, out)}
 
+    def train_stats(self, reset=True):
+        """Device time of the training kernels since the last reset (see nc_ctx_train_stats)."""
+        out = np.zeros(8, np.float64)
+        self._check(self.lib.nc_ctx_train_stats(self.h, out.ctypes.data, int(reset)))
+        keys = ("emission_ms", "fwbw_ms", "pm_stats_ms", "st_stats_ms", "events", "launches", "waves")
+        return {k: float(v) for k, v in zip(keys, out)}
+
     def set_viterbi_mode(self, mode):
         """L.NC_VIT_AUTO (alpha-column kernel where it fits) or L.NC_VIT_BACKPOINTER."""
         self._check(self.lib.nc_ctx_set_viterbi_mode(self.h, int(mode)))

@@ -95,6 +95,7 @@ void nc_ctx_destroy(nc_ctx* ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    for (cudaEvent_t e : ctx->evk) if (e) cudaEventDestroy(e);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream3) { cudaStreamSynchronize(ctx->stream3); cudaStreamDestroy(ctx->stream3); }
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);

@@ -47,6 +47,9 @@ struct nc_ctx
     size_t fb_scratch_limit = 0;  // bytes of E|alpha|beta slabs per wave (0 = pick from free memory)
     unsigned host_threads = 1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evk[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // around the four training kernels of a wave
+    double train_ms[4] = { 0, 0, 0, 0 };   // emission, fwbw, pm_stats, st_stats: device time since the last reset
+    double train_events = 0, train_launches = 0, train_waves = 0;
     float last_kernel_ms = 0.f;
     int last_launches = 0;        // kernels launched by the most recent nc_viterbi_packed
     unsigned long long* d_stats = nullptr;   // 8 counters of the alpha kernel (nc_ctx_viterbi_stats)

@@ -67,13 +67,15 @@ __device__ __forceinline__ float fold_logsum_in_order(float acc, const int n, Ge
 
 // One step of a long in-order p7_FLogsum chain: acc (warp-uniform) absorbs the 32 terms x (one per lane, lane order).
 // While acc >= x the step is acc' = acc + tbl[idx(acc - x)]: the lanes look their increments up with the value the
-// chain had at the START of the block, every lane then forms its own running value a_k = acc + t_0 + ... + t_{k-1}
-// (sequential float adds over the live lanes only, all lanes in lock step), and recomputes its index from a_k.  When
-// every index is confirmed the a_k are by induction the sequential chain's values and lane 31's a + t is the result;
-// otherwise the recomputed indices are the next guess (the first unconfirmed lane is certainly right then).  After
-// three rounds, or when a term exceeds the running value (start of a chain), the block is folded sequentially.
+// chain had at the START of the block, the live lanes' increments are compacted into a warp-private list, every lane
+// then forms its own running value a_k = acc + t_0 + ... + t_{k-1} (sequential float adds over the live terms below
+// it, all lanes in lock step: a chain of 4-cycle FADDs fed by broadcast loads), and recomputes its index from a_k.
+// When every index is confirmed the a_k are by induction the sequential chain's values and the last live lane's
+// a + t is the result; otherwise the recomputed indices are the next guess (the first unconfirmed lane is certainly
+// right then).  After three rounds, or when a term exceeds the running value (start of a chain), the block is folded
+// term by term.  lst: 36 floats, 16-byte aligned, private to the warp.
 template < typename TB >
-__device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl, const int lane)
+__device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl, const int lane, float* __restrict__ lst)
 {
     const bool live = !((x == NC_NEG_INF) || (acc > x && __fsub_rn(acc, x) >= 15.999f));
     const unsigned m = __ballot_sync(FULL, live);
@@ -82,21 +84,30 @@ __device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl,
     if (spec_ok)
     {
         const float INF = __int_as_float(0x7f800000);   // dead lanes: d = +inf selects the zero entry
+        const int L = __popc(m);
+        const int r = __popc(m & ((1u << lane) - 1u));   // live terms below this lane
+        const int last = 31 - __clz((int)m);
         unsigned e = tbl.addr(live ? __fsub_rn(acc, x) : INF);
 #pragma unroll 1
         for (int round = 0; round < 3; ++round)
         {
             const float t = tbl.load(e);
+            if (live) lst[r] = t;
+            if (lane < 4) lst[L + lane] = 0.0f;
+            __syncwarp();
             float a = acc;
-            for (unsigned mm = m; mm; mm &= mm - 1)
+            for (int k = 0; k < L; k += 4)
             {
-                const int k = __ffs(mm) - 1;
-                const float tk = __shfl_sync(FULL, t, k);
-                a = (k < lane) ? __fadd_rn(a, tk) : a;
+                const float4 v = *reinterpret_cast< const float4* >(lst + k);
+                a = (k + 0 < r) ? __fadd_rn(a, v.x) : a;
+                a = (k + 1 < r) ? __fadd_rn(a, v.y) : a;
+                a = (k + 2 < r) ? __fadd_rn(a, v.z) : a;
+                a = (k + 3 < r) ? __fadd_rn(a, v.w) : a;
             }
+            __syncwarp();
             const unsigned e2 = tbl.addr(live ? __fsub_rn(a, x) : INF);
             const bool ok = !live || (a >= x && e2 == e);
-            if (__all_sync(FULL, ok)) return __shfl_sync(FULL, __fadd_rn(a, t), 31);
+            if (__all_sync(FULL, ok)) return __shfl_sync(FULL, __fadd_rn(a, t), last);
             e = e2;
         }
     }
@@ -117,16 +128,29 @@ struct FbSmem
     unsigned item;
 };
 
-constexpr int ST_CHUNK = FB_THREADS - 3 * 32;   // 416 terms per chunk of st_stats_kernel (13 producer warps)
+constexpr int ST_PROD = FB_THREADS - 3 * 32;   // 416 producer threads of st_stats_kernel (13 warps)
+constexpr int ST_R = 6;                        // training k-mers per producer thread and event (6 x 416 >= 2160)
+constexpr int ST_P2 = 256;                     // live (event, k-mer) items per hand-over to the fold warps
+constexpr unsigned ST_DONE = 0xffffffffu;
 struct StSmem
 {
     float tbl[fb::TBL_N];
-    float term[2][3][ST_CHUNK];   // two buffers: computed by warps 3..15, folded by warps 0..2
+    float term[2][3][ST_P2];      // two hand-over buffers: terms of live items, in order
+    unsigned cnt[2];              // items in each buffer (ST_DONE: no more hand-overs)
+    unsigned short live[ST_R * ST_PROD];   // positions (in the training k-mer list) of the event's live items, ascending
+    unsigned wtot[13];            // live items per producer warp
+    float acc_snap[4];            // running values the fold warps published after their last hand-over
+    __align__(16) float lst[3][40];   // fold32's warp-private lists
     unsigned seq_id[NC_MAX_TRAIN_SEQS];      // the strand's sequences with >= 2 events, in order
     unsigned seq_first[NC_MAX_TRAIN_SEQS + 1];  // first flattened (event) index of each
     unsigned n_seq;
 };
 
+// posteriors are scaled by 2^64 inside pm_stats_kernel: powers of two commute with every rounding as long as nothing
+// underflows, and the scaled terms never do (p >= 2^-149 becomes >= 2^-85), so the six sums are the reference's sums
+// times 2^64, bit for bit, except that terms the reference computes as DENORMALS (p/sigma^2 below 2^-126: they cannot
+// influence a sum that contains one posterior above 2^-100) keep their full precision here
+constexpr float PM_SCALE = 18446744073709551616.0f;
 constexpr int PM_EV = 16;                 // events per CTA of pm_stats_kernel (= FB_EV_TILE)
 constexpr int PM_CHAINS = PM_EV * 6;      // 96 serial sums = the lanes of three warps
 constexpr int PM_ROW = PM_CHAINS + 1;     // row stride of the term buffer: producer lanes (consecutive states) hit different banks
@@ -340,7 +364,7 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
             for (int jl = 0; jl < nj; ++jl) acc = __fadd_rn(acc, T[jl * PM_ROW]);
         }
         const unsigned ev = (unsigned)t / 6u, s = (unsigned)t % 6u;
-        if (ev < n_ev) a.pm_stats[(Q.ev_out + i0 + ev) * 6 + s] = acc;
+        if (ev < n_ev) a.pm_stats[(Q.ev_out + i0 + ev) * 6 + s] = __fmul_rn(acc, 1.0f / PM_SCALE);
     }
     else
     {
@@ -358,6 +382,7 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
                 const float sg2 = __fmul_rn(sg, sg);
                 const float eta = __ldg(M + 2 * NC_N_STATES + j);
                 const float lam = __ldg(M + 3 * NC_N_STATES + j);
+                const float rsg2 = __frcp_rn(sg2), reta = __frcp_rn(eta);
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
                 {
@@ -366,13 +391,16 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
                     if (ev < n_ev)
                     {
                         const size_t o = (size_t)(i0 + ev) * NC_N_STATES + j;
-                        const float pst = nc_expf(__fsub_rn(__fadd_rn(__ldcs(AL + o), __ldcs(BE + o)), logz));
-                        ts0 = __fdiv_rn(pst, sg2);
+                        // the posterior, scaled by 2^64 (exact): every term below stays in the normal range, so the
+                        // correctly rounded divisions are three instructions (div_rn) instead of the IEEE division's
+                        // denormal slow path, which two thirds of the kernel's instructions used to be
+                        const float pst = __fmul_rn(nc_expf(__fsub_rn(__fadd_rn(__ldcs(AL + o), __ldcs(BE + o)), logz)), PM_SCALE);
+                        ts0 = div_rn(pst, sg2, rsg2);
                         ts1 = __fmul_rn(ts0, mu);
                         ts2 = __fmul_rn(ts1, mu);
                         tl0 = __fmul_rn(pst, lam);
-                        tl1 = __fdiv_rn(tl0, eta);
-                        tl2 = __fdiv_rn(tl1, eta);
+                        tl1 = div_rn(tl0, eta, reta);
+                        tl2 = div_rn(tl1, eta, reta);
                     }
                     float* R = T + 6 * ev;
                     R[0] = ts0; R[1] = ts1; R[2] = ts2; R[3] = tl0; R[4] = tl1; R[5] = tl2;
@@ -390,9 +418,17 @@ size_t pm_stats_smem_bytes() { return (size_t)2 * PM_JT * PM_ROW * sizeof(float)
 //   denom (+)= post(i,j1);  stay (+)= min(joint(j1->j1 | log p_stay), post);
 //   skip (+)= log(exp(post) - exp(min(d01, post))),  d01 = stay' (+) the 4 one-step joints with log(p_step/4)
 // over the strand's sequences in order, events i < n-1, the 2160 training k-mers in ascending order: ONE chain of
-// (events x 2160) terms per accumulator.  The chain is cut into chunks of 416 consecutive terms (chunks run across
-// event boundaries); warps 3..15 compute the terms of a chunk into one of two buffers while warps 0..2 fold the
-// previous chunk, one accumulator each, 32 terms per step (fold32).
+// (events x 2160) terms per accumulator, (+) = p7_FLogsum.
+//
+// A term more than 15.999 below the running value leaves it unchanged, and the three terms of a k-mer are bounded by its
+// log posterior (stay and skip are clamped to it; log(exp(.)) round trips stay within a few ulps).  So per event:
+//   phase 1  (13 producer warps, 6 k-mers per thread)  log posterior of every training k-mer, two loads each; a k-mer
+//            whose log posterior is 16.25 below the smallest of the three running values the fold warps last published
+//            (stale values are smaller, hence conservative) is dead for all three chains; the others are compacted, in
+//            order, into a list -- typically a tenth of the k-mers;
+//   phase 2  the full terms (five joint probabilities, p7_FLogsum, two expf, one logf) of the listed k-mers only, at
+//            most 256 per hand-over, into one of two buffers;
+//   fold     warps 0..2, one accumulator each, absorb the previous hand-over 32 terms per step (fold32) meanwhile.
 __global__ void __launch_bounds__(FB_THREADS, 3) st_stats_kernel(const FbArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -416,23 +452,23 @@ __global__ void __launch_bounds__(FB_THREADS, 3) st_stats_kernel(const FbArgs a)
         ss.seq_first[ns] = first;
         ss.n_seq = ns;
     }
+    if (t < 4) ss.acc_snap[t] = NC_NEG_INF;
     __syncthreads();
     const fb::TblSmem tbl = fb::make_tbl_smem(ss.tbl);
-    const unsigned n_km = a.n_train_kmers;
+    const unsigned n_km = a.n_train_kmers;   // <= ST_R * ST_PROD (checked on the host)
     const unsigned n_seq = ss.n_seq;
-    const unsigned long long n_items = (unsigned long long)ss.seq_first[n_seq] * n_km;
-    const unsigned n_chunks = (unsigned)((n_items + ST_CHUNK - 1) / ST_CHUNK);
-    const float log_p_stay = G.log_p_stay[st];
-    const float log_p_step_4 = G.log_p_step_4[st];
+    const unsigned n_ev = ss.seq_first[n_seq];
 
-    auto compute = [&](unsigned chunk, float (*term)[ST_CHUNK]) {
-        const int ct = t - 3 * 32;   // 0..415
-        const unsigned long long item = (unsigned long long)chunk * ST_CHUNK + (unsigned)ct;
-        float t_denom = NC_NEG_INF, t_stay = NC_NEG_INF, t_skip = NC_NEG_INF;
-        if (item < n_items)
+    if (warp >= 3)
+    {
+        // ================================================= producers
+        const int pt = t - 3 * 32, pw = warp - 3;
+        const float log_p_stay = G.log_p_stay[st];
+        const float log_p_step_4 = G.log_p_step_4[st];
+        int buf = 0;
+        unsigned s = 0;
+        for (unsigned ef = 0; ef < n_ev; ++ef)
         {
-            const unsigned ef = (unsigned)(item / n_km), km = (unsigned)(item - (unsigned long long)ef * n_km);
-            unsigned s = 0;
             while (s + 1 < n_seq && ef >= ss.seq_first[s + 1]) ++s;
             const unsigned sq = ss.seq_id[s], i = ef - ss.seq_first[s];
             const FbSeq& Q = a.seqs[sq];
@@ -445,59 +481,113 @@ __global__ void __launch_bounds__(FB_THREADS, 3) st_stats_kernel(const FbArgs a)
             const float* Bi = BE + (size_t)i * NC_N_STATES;
             const float* Bn = BE + (size_t)(i + 1) * NC_N_STATES;
             const float* En = E + (size_t)(i + 1) * NC_N_STATES;
-            const unsigned j1 = __ldg(a.train_kmers + km);
-            const unsigned nb = (j1 & 1023u) << 2;   // the four one-step successors are one aligned float4
-            const float al = __ldg(Ai + j1), bi = __ldg(Bi + j1), en = __ldg(En + j1), bn = __ldg(Bn + j1);
-            const float4 e4 = __ldg(reinterpret_cast< const float4* >(En + nb));
-            const float4 b4 = __ldg(reinterpret_cast< const float4* >(Bn + nb));
-            const float log_p_j1 = __fsub_rn(__fadd_rn(al, bi), logz);
-            // joint(i, j1, j2, lt) = alpha + lt + emission(j2, e_{i+1}) + beta(i+1, j2) - logZ   (:457-469)
-            float jj = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_stay), en), bn), logz);
-            if (jj > log_p_j1) jj = log_p_j1;
-            float s2 = flogsum(NC_NEG_INF, jj, tbl);
-            const float ev[4] = { e4.x, e4.y, e4.z, e4.w }, bv[4] = { b4.x, b4.y, b4.z, b4.w };
+            // ---- phase 1
+            const float smin = fminf(fminf(ss.acc_snap[0], ss.acc_snap[1]), ss.acc_snap[2]);
+            float av[ST_R], bv[ST_R];
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
+            for (int r = 0; r < ST_R; ++r)
             {
-                const float jv = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_step_4), ev[b]), bv[b]), logz);
-                s2 = flogsum(s2, jv, tbl);
+                const unsigned km = (unsigned)(ST_R * pt + r);
+                if (km < n_km)
+                {
+                    const unsigned j1 = __ldg(a.train_kmers + km);
+                    av[r] = __ldg(Ai + j1);
+                    bv[r] = __ldg(Bi + j1);
+                }
+                else av[r] = bv[r] = NC_NEG_INF;
             }
-            if (s2 > log_p_j1) s2 = log_p_j1;
-            const float p2 = __fsub_rn(nc_expf(log_p_j1), nc_expf(s2));
-            t_denom = log_p_j1;
-            t_stay = jj;
-            t_skip = nc_logf(p2);
-        }
-        term[0][ct] = t_denom;
-        term[1][ct] = t_stay;
-        term[2][ct] = t_skip;
-    };
-
-    if (n_chunks && warp >= 3) compute(0, ss.term[0]);
-    __syncthreads();
-    float acc = NC_NEG_INF;   // warps 0..2: denom, stay, skip
-    for (unsigned c = 0; c < n_chunks; ++c)
-    {
-        const int buf = (int)(c & 1u);
-        if (warp >= 3)
-        {
-            if (c + 1 < n_chunks) compute(c + 1, ss.term[buf ^ 1]);
-        }
-        else
-        {
-            const float* Tw = ss.term[buf][warp];
-            float x = Tw[lane];
-#pragma unroll 1
-            for (int base = 0; base < ST_CHUNK; base += 32)
+            unsigned flags = 0;
+#pragma unroll
+            for (int r = 0; r < ST_R; ++r)
             {
-                const float xn = (base + 32 < ST_CHUNK) ? Tw[base + 32 + lane] : NC_NEG_INF;
-                acc = fold32(acc, x, tbl, lane);
-                x = xn;
+                const float lp = __fsub_rn(__fadd_rn(av[r], bv[r]), logz);
+                const bool live = !((lp == NC_NEG_INF) || (smin > lp && __fsub_rn(smin, lp) >= 16.25f));
+                flags |= live ? (1u << r) : 0u;
+            }
+            const unsigned mine = __popc(flags);
+            unsigned incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const unsigned v = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane == 31) ss.wtot[pw] = incl;
+            asm volatile("bar.sync 1, 416;" ::: "memory");
+            unsigned wbase = 0, n_live = 0;
+#pragma unroll
+            for (int w = 0; w < 13; ++w)
+            {
+                const unsigned c = ss.wtot[w];
+                wbase += (w < pw) ? c : 0u;
+                n_live += c;
+            }
+            {
+                unsigned pos = wbase + incl - mine;
+#pragma unroll
+                for (int r = 0; r < ST_R; ++r)
+                    if (flags & (1u << r)) ss.live[pos++] = (unsigned short)(ST_R * pt + r);
+            }
+            asm volatile("bar.sync 1, 416;" ::: "memory");
+            // ---- phase 2
+            for (unsigned b0 = 0; b0 < n_live; b0 += ST_P2)
+            {
+                const unsigned q = b0 + (unsigned)pt;
+                if (pt < ST_P2 && q < n_live)
+                {
+                    const unsigned j1 = __ldg(a.train_kmers + ss.live[q]);
+                    const unsigned nb = (j1 & 1023u) << 2;   // the four one-step successors are one aligned float4
+                    const float al = __ldg(Ai + j1), bi = __ldg(Bi + j1), en = __ldg(En + j1), bn = __ldg(Bn + j1);
+                    const float4 e4 = __ldg(reinterpret_cast< const float4* >(En + nb));
+                    const float4 b4 = __ldg(reinterpret_cast< const float4* >(Bn + nb));
+                    const float log_p_j1 = __fsub_rn(__fadd_rn(al, bi), logz);
+                    // joint(i, j1, j2, lt) = alpha + lt + emission(j2, e_{i+1}) + beta(i+1, j2) - logZ   (:457-469)
+                    float jj = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_stay), en), bn), logz);
+                    if (jj > log_p_j1) jj = log_p_j1;
+                    float s2 = flogsum(NC_NEG_INF, jj, tbl);
+                    const float ev[4] = { e4.x, e4.y, e4.z, e4.w }, bv4[4] = { b4.x, b4.y, b4.z, b4.w };
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                    {
+                        const float jv = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_step_4), ev[b]), bv4[b]), logz);
+                        s2 = flogsum(s2, jv, tbl);
+                    }
+                    if (s2 > log_p_j1) s2 = log_p_j1;
+                    const float p2 = __fsub_rn(nc_expf(log_p_j1), nc_expf(s2));
+                    ss.term[buf][0][pt] = log_p_j1;
+                    ss.term[buf][1][pt] = jj;
+                    ss.term[buf][2][pt] = nc_logf(p2);
+                }
+                if (pt == 0) ss.cnt[buf] = min((unsigned)ST_P2, n_live - b0);
+                __syncthreads();   // hand-over (the fold warps wait here too)
+                buf ^= 1;
             }
         }
+        if (pt == 0) ss.cnt[buf] = ST_DONE;
         __syncthreads();
     }
-    if (warp < 3 && lane == 0) a.st_stats[(grp * 2 + st) * 3 + warp] = acc;   // denom, stay, skip
+    else
+    {
+        // ================================================= fold warps: denom, stay, skip
+        float acc = NC_NEG_INF;
+        int buf = 0;
+        for (;;)
+        {
+            __syncthreads();
+            const unsigned n_items = ss.cnt[buf];
+            if (n_items == ST_DONE) break;
+            const float* Tw = ss.term[buf][warp];
+#pragma unroll 1
+            for (unsigned base = 0; base < n_items; base += 32)
+            {
+                const float x = (base + lane < n_items) ? Tw[base + lane] : NC_NEG_INF;
+                acc = fold32(acc, x, tbl, lane, ss.lst[warp]);
+            }
+            if (lane == 0) ss.acc_snap[warp] = acc;
+            buf ^= 1;
+        }
+        if (lane == 0) a.st_stats[(grp * 2 + st) * 3 + warp] = acc;   // denom, stay, skip
+    }
 }
 
 } // namespace nc

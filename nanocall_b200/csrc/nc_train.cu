@@ -241,22 +241,32 @@ int run_wave(nc_ctx* ctx, const Wave& w, const float* d_mean, const float* d_std
     a.log_n_states = std::log((float)NC_N_STATES);
 
     const unsigned tiles = (w.max_len + nc::FB_EV_TILE - 1) / nc::FB_EV_TILE;
+    for (int k = 0; k < 5; ++k)
+        if (!ctx->evk[k]) NC_CUDA(ctx, cudaEventCreate(&ctx->evk[k]));
     NC_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    NC_CUDA(ctx, cudaEventRecord(ctx->evk[0], s));
     nc::emission_kernel<<< dim3(tiles, ns), 512, 0, s >>>(a);
     NC_CUDA(ctx, cudaGetLastError());
+    NC_CUDA(ctx, cudaEventRecord(ctx->evk[1], s));
     const unsigned grid = std::min< unsigned >(ns, 2u * (unsigned)ctx->prop.multiProcessorCount);
     nc::fwbw_kernel<<< grid, 512, nc::fwbw_smem_bytes(), s >>>(a);
     NC_CUDA(ctx, cudaGetLastError());
+    NC_CUDA(ctx, cudaEventRecord(ctx->evk[2], s));
+    int launches = 2;
     if (pm_stats)
     {
         nc::pm_stats_kernel<<< dim3(tiles, ns), 512, nc::pm_stats_smem_bytes(), s >>>(a);
         NC_CUDA(ctx, cudaGetLastError());
+        ++launches;
     }
+    NC_CUDA(ctx, cudaEventRecord(ctx->evk[3], s));
     if (st_stats && ng)
     {
         nc::st_stats_kernel<<< dim3(ng, 2), 512, nc::st_stats_smem_bytes(), s >>>(a);
         NC_CUDA(ctx, cudaGetLastError());
+        ++launches;
     }
+    NC_CUDA(ctx, cudaEventRecord(ctx->evk[4], s));
     NC_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     lz.resize(ns);
     NC_CUDA(ctx, cudaMemcpyAsync(lz.data(), ctx->fb_lz.p, ns * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -274,6 +284,15 @@ int run_wave(nc_ctx* ctx, const Wave& w, const float* d_mean, const float* d_std
     float ms = 0.f;
     NC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_kernel_ms = ms;
+    for (int k = 0; k < 4; ++k)
+    {
+        float kms = 0.f;
+        NC_CUDA(ctx, cudaEventElapsedTime(&kms, ctx->evk[k], ctx->evk[k + 1]));
+        ctx->train_ms[k] += kms;
+    }
+    ctx->train_events += (double)w.n_events;
+    ctx->train_launches += launches;
+    ctx->train_waves += 1;
     return NC_OK;
 }
 
@@ -355,6 +374,8 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
         if (ev_off[s + 1] <= ev_off[s]) NC_FAIL(ctx, NC_ERR_ARG, "nc_train_round_batch: sequence %u has no events", s);
         if (seq_strand[s] > 1) NC_FAIL(ctx, NC_ERR_ARG, "nc_train_round_batch: sequence %u: strand must be 0 or 1", s);
     }
+    if (ctx->n_train_kmers > 6u * 416u)   // st_stats_kernel: 6 training k-mers per producer thread (2160 for 6-mers)
+        NC_FAIL(ctx, NC_ERR_STATE, "nc_train_round_batch: %u training k-mers exceed the kernel's 2496", ctx->n_train_kmers);
     const uint64_t base = ev_off[0];
     const size_t total = ev_off[n_seqs] - base;
     std::vector< float > yfix;
@@ -442,6 +463,22 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
         g0 = g1;
     }
     ctx->last_kernel_ms = kernel_ms;
+    return NC_OK;
+}
+
+int nc_ctx_train_stats(nc_ctx* ctx, double* out8, int reset)
+{
+    if (!ctx || !out8) return NC_ERR_ARG;
+    for (int k = 0; k < 4; ++k) out8[k] = ctx->train_ms[k];
+    out8[4] = ctx->train_events;
+    out8[5] = ctx->train_launches;
+    out8[6] = ctx->train_waves;
+    out8[7] = 0;
+    if (reset)
+    {
+        for (int k = 0; k < 4; ++k) ctx->train_ms[k] = 0;
+        ctx->train_events = ctx->train_launches = ctx->train_waves = 0;
+    }
     return NC_OK;
 }
 

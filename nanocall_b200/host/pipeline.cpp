@@ -116,22 +116,35 @@ void Pipeline::init_models()
                                   << ", stdv=" << m.stdv << "]");
         models_[name] = std::move(m);
     };
-    if (!opt_.model_files.empty())
+    // -m strand:file (multi) and --model-fofn (one "strand:file" per line), nanocall.cpp:99-153
+    std::vector< std::string > specs = opt_.model_files;
+    if (!opt_.model_fofn.empty())
     {
-        bool have[3] = { false, false, false };
-        for (const auto& s : opt_.model_files)
+        std::ifstream is(opt_.model_fofn);
+        if (!is) throw std::runtime_error("cannot open " + opt_.model_fofn);
+        std::string line;
+        while (std::getline(is, line)) specs.push_back(line);
+    }
+    if (!specs.empty())
+    {
+        std::vector< std::string > by_strand[3];
+        for (const auto& s : specs)
         {
             if (s.size() < 3 || (s[0] != '0' && s[0] != '1' && s[0] != '2') || s[1] != ':')
                 throw std::runtime_error("could not parse model name: \"" + s + "\"; format should be \"[0|1|2]:<file>\"");
-            int st = s[0] - '0';
-            have[st] = true;
-            std::vector< float > table;
-            std::string err;
-            if (!read_model_tsv(s.substr(2), table, err)) throw std::runtime_error(err);
-            add(s.substr(2), st, std::move(table));
+            by_strand[s[0] - '0'].push_back(s.substr(2));
         }
-        if (!have[2] && (have[0] != have[1]))
-            throw std::runtime_error("models were specified only for one strand! give models for both strands, or for neither.");
+        if (by_strand[2].empty() && (by_strand[0].empty() != by_strand[1].empty()))
+            throw std::runtime_error(std::string("models were specified only for strand ") + (by_strand[0].empty() ? "1" : "0")
+                                     + "! give models for both strands, or for neither.");
+        for (int st = 0; st < 3; ++st)
+            for (const auto& f : by_strand[st])
+            {
+                std::vector< float > table;
+                std::string err;
+                if (!read_model_tsv(f, table, err)) throw std::runtime_error(err);
+                add(f, st, std::move(table));
+            }
         return;
     }
     // builtin models: names filtered by "<pore>." prefix (nanocall.cpp:157-170)
@@ -161,9 +174,9 @@ void Pipeline::init_read_params(Read& r) const
     r.pm_params_m.clear();
     r.st_params_m.clear();
     for (auto& k : r.preferred_model) k = Model_Key();
+    if (r.num_ed_events == 0) return;
     const nc_st_params dst = default_st();
-    r.scale_strands_together = opt_.double_strand_scaling
-        && r.events[0].size() >= opt_.min_ed_events && r.events[1].size() >= opt_.min_ed_events;
+    // r.scale_strands_together was decided by the loader from the RAW strand bounds (Fast5_Summary.hpp:210-212)
     if (r.scale_strands_together)
     {
         float m0, s0, m1, s1;
@@ -604,22 +617,22 @@ void Pipeline::write_output(std::ostream& os, const Read& r) const
 
 void Pipeline::write_stats_header(std::ostream& os)
 {
-    // Fast5_Summary::write_tsv_header (Fast5_Summary.hpp:460-476)
+    // Fast5_Summary::write_tsv_header (Fast5_Summary.hpp:460-476) + the endl of nanocall.cpp:896
     os << "file_name\tread_name\tnum_ed_events\tabasic_level\ttemplate_start_idx\ttemplate_end_idx"
        << "\tcomplement_start_idx\tcomplement_end_idx";
     for (unsigned st = 0; st < 2; ++st)
         os << "\tn" << st << "_model_name\tn" << st << "_scale\tn" << st << "_shift\tn" << st << "_drift\tn" << st
            << "_var\tn" << st << "_scale_sd\tn" << st << "_var_sd\tn" << st << "_p_stay\tn" << st << "_p_skip";
-    os << "\n";
+    os << std::endl;
 }
 
-void Pipeline::write_stats(std::ostream& os, const Read& r) const
+void Pipeline::write_stats(std::ostream& os, const Read& r, const Options& opt)
 {
-    // Fast5_Summary::write_tsv (:478-502).  Event tables carry no raw-event indices: the strand bounds are the
-    // offsets of the two strands in the concatenated table, abasic_level is 0.
-    const size_t n0 = r.events[0].size(), n1 = r.events[1].size();
-    os << r.base_file_name << '\t' << r.read_id << '\t' << (n0 + n1) << '\t' << 0 << '\t' << 0 << '\t' << n0 << '\t' << n0
-       << '\t' << (n0 + n1);
+    // Fast5_Summary::write_tsv (:478-502).  The parameter columns switch the stream to fixed notation with five
+    // decimals (Pore_Model.hpp:72-76) and the reference never switches back, so abasic_level is printed in the default
+    // notation in the first row only: the stream state is deliberately left as the reference leaves it.
+    os << r.base_file_name << '\t' << r.read_id << '\t' << r.num_ed_events << '\t' << r.abasic_level << '\t' << r.strand_bounds[0]
+       << '\t' << r.strand_bounds[1] << '\t' << r.strand_bounds[2] << '\t' << r.strand_bounds[3];
     auto pm_tsv = [&](const nc_pm_params& p) {
         os << std::fixed << std::setprecision(5) << p.scale << '\t' << p.shift << '\t' << p.drift << '\t' << p.var << '\t'
            << p.scale_sd << '\t' << p.var_sd;
@@ -628,7 +641,7 @@ void Pipeline::write_stats(std::ostream& os, const Read& r) const
     for (unsigned st = 0; st < 2; ++st)
     {
         os << '\t';
-        if (!r.preferred_model[st][st].empty() && r.pm_params_m.count(r.preferred_model[st]))
+        if (!r.preferred_model[st][st].empty())
         {
             os << r.preferred_model[st][st] << '\t';
             pm_tsv(r.pm_params_m.at(r.preferred_model[st]));
@@ -640,11 +653,13 @@ void Pipeline::write_stats(std::ostream& os, const Read& r) const
             os << ".\t";
             pm_tsv(default_pm());
             os << '\t';
-            st_tsv(default_st());
+            nc_st_params d;
+            d.p_stay = opt.pr_stay;
+            d.p_skip = opt.pr_skip;
+            st_tsv(d);
         }
     }
-    os << "\n";
-    os.unsetf(std::ios_base::floatfield);
+    os << std::endl;
 }
 
 // ---------------------------------------------------------------- event tables
@@ -652,6 +667,15 @@ void Pipeline::write_stats(std::ostream& os, const Read& r) const
 // reaches the abasic level or whose stdv exceeds 4 before it builds the strands' event sequences (:352-363).  Event
 // tables are the input here, so the same rule is applied on load; the abasic level is known only when the table
 // carries it ("#abasic_level <pA>"), otherwise that half of the rule is off.
+// segmented tables carry no raw-event indices: the strand bounds are the offsets of the two strands in the
+// concatenated table, the abasic level is unknown (0)
+static void finish_segmented_read(Read& r)
+{
+    const unsigned n0 = (unsigned)r.events[0].size(), n1 = (unsigned)r.events[1].size();
+    r.num_ed_events = n0 + n1;
+    r.strand_bounds = { { 0u, n0, n0, n0 + n1 } };
+}
+
 static bool keep_event(float mean, float stdv, float abasic_level)
 {
     if (mean >= abasic_level) return false;
@@ -700,6 +724,7 @@ bool load_events_tsv(const std::string& path, Read& r, std::string& err)
         Strand_Events& ev = r.events[st];
         ev.mean.push_back(mean); ev.stdv.push_back(stdv); ev.start.push_back(start); ev.length.push_back(length);
     }
+    finish_segmented_read(r);
     return true;
 }
 
@@ -749,6 +774,7 @@ bool load_events_ncev(const std::string& path, std::vector< Read >& reads, std::
                 }
             for (std::vector< float >* v : { &ev.mean, &ev.stdv, &ev.start, &ev.length }) v->resize(w);
         }
+        finish_segmented_read(r);
         reads.push_back(std::move(r));
     }
     return true;

@@ -28,6 +28,13 @@ struct Options
 {
     // defaults = nanocall.cpp:56-94
     unsigned min_ed_events = 10;
+    unsigned max_ed_events = 100000;
+    std::array< unsigned, 4 > trim_margins{ { 50u, 50u, 50u, 50u } };  // after start, before end, before hairpin, after hairpin
+    bool template_only = false;            // --1d
+    double abasic_level_top_percent = 1.0; // Fast5_Summary.hpp:92-104, set by the pore preset (nanocall.cpp:943-969)
+    double abasic_level_top_offset = -1.0; // -1: by pore preset (r73 -> 5, r9 -> 0)
+    std::string ed_group;                  // accepted for compatibility: event tables hold one EventDetection group
+    unsigned chunk_size = 1;               // accepted for compatibility: batching replaces pfor's chunks
     unsigned fasta_line_width = 80;
     float scaling_select_threshold = 20.0f;
     float scaling_min_progress = 1.0f;
@@ -44,6 +51,8 @@ struct Options
     int train_drift = -1;          // -1: by pore preset (r73 -> 1, r9 -> 0; nanocall.cpp:943-969)
     int log_level = 2;             // 0 error, 1 warning, 2 info, 3 debug
     std::vector< std::string > model_files;  // "strand:file"
+    std::string model_fofn;        // file of "strand:file" lines (nanocall.cpp:118-127)
+    std::string trans_fn;          // custom initial state transitions (nanocall.cpp:180-193)
     std::string data_dir;          // where builtin_models.{bin,txt} live
 };
 
@@ -57,6 +66,12 @@ struct Read
 {
     std::string read_id;
     std::string base_file_name;
+    // Fast5_Summary fields (Fast5_Summary.hpp:30-43).  num_ed_events == 0: the read is skipped by training and
+    // basecalling (nanocall.cpp:293,623) but keeps its --stats row.
+    unsigned num_ed_events = 0;
+    float abasic_level = 0.f;
+    float sampling_rate = 0.f;
+    std::array< unsigned, 4 > strand_bounds{ { 0u, 0u, 0u, 0u } };
     Strand_Events events[2];
     bool scale_strands_together = false;
     std::array< Model_Key, 3 > preferred_model;                            // Fast5_Summary.hpp:32-34
@@ -92,7 +107,7 @@ public:
     static void write_fasta(std::ostream& os, const std::string& name, const std::string& seq, unsigned width);
     void write_output(std::ostream& os, const Read& r) const;
     static void write_stats_header(std::ostream& os);
-    void write_stats(std::ostream& os, const Read& r) const;
+    static void write_stats(std::ostream& os, const Read& r, const Options& opt);
 
     const std::map< std::string, Model >& models() const { return models_; }
     nc_ctx* ctx() { return ctx_; }

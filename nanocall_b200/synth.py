@@ -134,3 +134,51 @@ def make_batch_uniform(seed, table, n_reads, n_events, p_stay=0.1, p_skip=0.3, l
     off = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(n_events))
     return {"ev_off": off, "mean": mean, "stdv": stdv, "start": start.astype(np.float32).reshape(-1),
             "truth": states}
+
+
+def make_raw_2d_read(rng, tables, nt, nc, params, sampling_rate=5000.0, lead=60, tail=60, hairpin=8, comp=0,
+                     hairpin_level=115.0):
+    """One raw 2D read as a fast5 file holds it (structured array: mean, stdv as float64, start, length in samples):
+    lead-in, template (nt events), a hairpin island of abasic-level events, complement (nc events), tail.
+    tables = (template table, [complement tables]); params = the read's scaling, applied with the time base the
+    reference uses when both strands are scaled together (seconds from the template's first event).
+    nc == 0: a 1D read without hairpin."""
+    from .evio import RAW_DTYPE
+    parts = []
+    clock = 1000
+
+    def strand(table, n, pm, t0_ref):
+        nonlocal clock
+        rd = make_read(rng, table, n, IDENTITY_PARAMS)
+        length = np.maximum(10, np.rint(np.maximum(0.002, rng.exponential(0.02, n)) * sampling_rate)).astype(np.int64)
+        start = clock + np.concatenate([[0], np.cumsum(length)[:-1]])
+        t0 = start[0] if t0_ref is None else t0_ref
+        t = (start - t0) / sampling_rate
+        tb = table[rd["states"]].astype(np.float64)
+        scale, shift, drift, var, scale_sd, var_sd = [float(v) for v in pm]
+        mean = rng.normal(scale * tb[:, 0] + shift + drift * t, var * tb[:, 1]).astype(np.float32)
+        lam = tb[:, 2] ** 3 / tb[:, 3] ** 2
+        stdv = np.clip(rng.wald(scale_sd * tb[:, 2], var_sd * lam), 1e-3, 4.0).astype(np.float32)
+        ev = np.zeros(n, RAW_DTYPE)
+        ev["mean"], ev["stdv"], ev["start"], ev["length"] = mean, stdv, start, length
+        clock = int(start[-1] + length[-1])
+        return ev, int(t0)
+
+    ttab, ctabs = tables
+    ev, _ = strand(ttab, lead, IDENTITY_PARAMS, None)
+    parts.append(ev)
+    ev, t0 = strand(ttab, nt, params, None)
+    parts.append(ev)
+    if nc:
+        h = np.zeros(hairpin, RAW_DTYPE)
+        h["mean"] = (hairpin_level + 2.0 * rng.standard_normal(hairpin)).astype(np.float32)
+        h["stdv"] = (1.0 + 0.2 * rng.random(hairpin)).astype(np.float32)
+        h["length"] = 100
+        h["start"] = clock + 100 * np.arange(hairpin)
+        clock += 100 * hairpin
+        parts.append(h)
+        ev, _ = strand(ctabs[comp], nc, params, t0)
+        parts.append(ev)
+    ev, _ = strand(ctabs[comp] if nc else ttab, tail, IDENTITY_PARAMS, None)
+    parts.append(ev)
+    return np.concatenate(parts)
