@@ -61,6 +61,9 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
         return fail("cudaFuncSetAttribute(viterbi_alpha_kernel)", e);
     if ((e = cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(stats)", e);
     if ((e = cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset(stats)", e);
+    if ((e = cudaMalloc(&ctx->d_abort, sizeof(unsigned))) != cudaSuccess) return fail("cudaMalloc(abort)", e);
+    if ((e = cudaHostAlloc(&ctx->h_abort, sizeof(unsigned), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc(abort)", e);
+    if (const char* v = std::getenv("NC_WAIT_LIMIT_S")) ctx->wait_limit_s = std::max(1e-3, std::atof(v));
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
@@ -90,6 +93,8 @@ void nc_ctx_destroy(nc_ctx* ctx)
     if (ctx->d_models) cudaFree(ctx->d_models);
     if (ctx->d_bp) cudaFree(ctx->d_bp);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->d_abort) cudaFree(ctx->d_abort);
+    if (ctx->h_abort) cudaFreeHost(ctx->h_abort);
     if (ctx->d_logsum_tbl) cudaFree(ctx->d_logsum_tbl);
     if (ctx->d_train_kmers) cudaFree(ctx->d_train_kmers);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -248,6 +253,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     auto tb_ctas_for = [&](size_t fwd) { return want_path ? std::max< size_t >(1, std::min< size_t >(4, (fwd + 24) / 48)) : (size_t)0; };
     auto fwd_ctas_in = [&](size_t ctas, size_t n_alpha_jobs) {   // forward CTAs when `ctas` SMs serve n_alpha_jobs jobs
         size_t fwd = std::min< size_t >(n_alpha_jobs, ctas);
+        fwd = std::min< size_t >(fwd, nc::viterbi_alpha_max_forward_ctas());   // the allocator's extent list holds them all
         while (fwd > 1 && fwd + tb_ctas_for(fwd) > ctas) --fwd;
         return fwd;
     };
@@ -387,6 +393,9 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     a.tb_tail = a.tb_head = a.slab_free = nullptr;
     a.colalloc = nullptr;
     a.stats = ctx->d_stats;
+    a.abort_word = ctx->d_abort;
+    a.wait_limit = (long long)(ctx->wait_limit_s * 1e3 * (double)ctx->prop.clockRate);   // clockRate is in kHz
+    NC_CUDA_INFLIGHT(cudaMemsetAsync(ctx->d_abort, 0, sizeof(unsigned), s));
 
     a.landed = nullptr;
     a.ev_total = total;
@@ -492,13 +501,21 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
             b.slab_free = b.tb_tail + 2;
             b.colalloc = (char*)ctx->tb.p + tk_bytes + ctl_bytes;
         }
-        nc::viterbi_alpha_kernel<<< fwd_a + tb_a, nc::VIT_THREADS, nc::viterbi_alpha_smem_bytes(), s >>>(b);
-        NC_CUDA_INFLIGHT(cudaGetLastError());
+        // Cooperative launch: forward CTAs and traceback service CTAs wait for each other, so the whole grid must be
+        // resident at once.  The driver guarantees that for a cooperative grid and REFUSES the launch (an error, not a
+        // hang) when it cannot: too many CTAs for the SMs this context can use.  SMs busy with other work (the
+        // backpointer kernel of this call, another context's kernels) only delay the start.
+        {
+            void* kargs[] = { (void*)&b };
+            NC_CUDA_INFLIGHT(cudaLaunchCooperativeKernel((const void*)nc::viterbi_alpha_kernel, dim3(fwd_a + tb_a), dim3(nc::VIT_THREADS),
+                                                         kargs, nc::viterbi_alpha_smem_bytes(), s));
+        }
         ++ctx->last_launches;
         if (n_long) NC_CUDA_INFLIGHT(cudaStreamWaitEvent(s, ctx->ev2, 0));
     }
     NC_CUDA_INFLIGHT(cudaEventRecord(ctx->ev1, s));
 
+    NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->h_abort, ctx->d_abort, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     NC_CUDA_INFLIGHT(cudaMemcpyAsync(path_logprob, ctx->path.p, n_jobs * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (mem == NC_MEM_HOST)
     {
@@ -508,6 +525,14 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     NC_CUDA_INFLIGHT(cudaStreamSynchronize(s));
     if (stream_in) NC_CUDA_INFLIGHT(cudaStreamSynchronize(ctx->stream3));
     NC_CUDA_INFLIGHT(cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
+    if (*ctx->h_abort != 0u)
+    {
+        static const char* const why[] = { "", "a forward CTA waited for its release slot", "a forward CTA waited for alpha columns",
+                                           "a traceback warp waited for a ticket", "the column allocator's extent list overflowed" };
+        const unsigned code = *ctx->h_abort;
+        NC_FAIL(ctx, NC_ERR_STATE, "nc_viterbi_packed: the alpha-column kernel stopped without finishing (%s for more than %.0f s): "
+                "results of this call are invalid", code < 5 ? why[code] : "unknown reason", ctx->wait_limit_s);
+    }
     return NC_OK;
 #undef NC_CUDA_INFLIGHT
 }

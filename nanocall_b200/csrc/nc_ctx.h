@@ -53,6 +53,9 @@ struct nc_ctx
     float last_kernel_ms = 0.f;
     int last_launches = 0;        // kernels launched by the most recent nc_viterbi_packed
     unsigned long long* d_stats = nullptr;   // 8 counters of the alpha kernel (nc_ctx_viterbi_stats)
+    unsigned* d_abort = nullptr;             // abort word of the alpha kernel's persistent grid (VitArgs::abort_word)
+    unsigned* h_abort = nullptr;             // pinned copy read back after every launch
+    double wait_limit_s = 120.0;             // NC_WAIT_LIMIT_S
     int vit_mode = 0;             // 0 = auto, 2 = backpointer kernel only (nc_ctx_set_viterbi_mode)
 };
 

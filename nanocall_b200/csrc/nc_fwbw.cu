@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
             {
                 const unsigned code = fb::bwd_lane_code(t, k);
                 const unsigned c0 = __shfl_sync(FULL, code, 0);
-                if (__all_sync(FULL, code == c0)) C.paths |= c0 << (2 * k);
+                if (__all_sync(FULL, code == c0)) C.paths |= c0 << (3 * k);
             }
             // beta[n-1] = 0
 #pragma unroll

@@ -226,16 +226,19 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
     const float NI = neg_inf();
     const unsigned F = C.flags;
     const bool oBef0 = F & 1u, oBef1 = F & 2u, oEq0 = F & 4u, oEq1 = F & 8u;
-    const float* At = A + C.offT;
-    const float* Ao = A + C.offO;
+    const float* pT = A + C.offT;   // T_s, advanced by 320 floats per slot
+    const float* pO = A + C.offO;   // the O pair of the next one-step slot, advanced by 1280 floats per such slot
+    int so = C.c;                   // the next one-step slot
     float P0 = NI, P1 = NI;
     // ---- slots below the self slot: one chain per half
-    for (int s = 0; s < C.sS; ++s)
+    for (int s = 0; s < C.sS; ++s, pT += 320)
     {
-        const float xT = fadd(C.wT, At[320 * s]);
-        if ((s & 3) == C.c)
+        const float xT = fadd(C.wT, *pT);
+        if (s == so)
         {
-            const float2 o = *reinterpret_cast< const float2* >(Ao + 1280 * (s >> 2));
+            const float2 o = *reinterpret_cast< const float2* >(pO);
+            so += 4;
+            pO += 1280;
             const float xO0 = fadd(C.wO[0], o.x), xO1 = fadd(C.wO[1], o.y);
             const float a0 = oBef0 ? xO0 : (oEq0 ? NI : xT), b0 = oBef0 ? xT : xO0;
             const float a1 = oBef1 ? xO1 : (oEq1 ? NI : xT), b1 = oBef1 ? xT : xO1;
@@ -251,12 +254,14 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
     // ---- the self slot: per state
     float acc[8];
     {
-        const int s = C.sS;
-        const float xT = fadd(C.wT, At[320 * s]);
-        if ((s & 3) == C.c)
+        const float xT = fadd(C.wT, *pT);
+        pT += 320;
+        if (C.sS == so)
         {
             // T, O and self share the slot: five folds, the three that are not self's position fold -inf
-            const float2 o = *reinterpret_cast< const float2* >(Ao + 1280 * (s >> 2));
+            const float2 o = *reinterpret_cast< const float2* >(pO);
+            so += 4;
+            pO += 1280;
             const float xO0 = fadd(C.wO[0], o.x), xO1 = fadd(C.wO[1], o.y);
 #ifdef __CUDA_ARCH__
 #pragma unroll
@@ -296,12 +301,14 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
         }
     }
     // ---- slots above the self slot: per state
-    for (int s = C.sS + 1; s < 16; ++s)
+    for (int s = C.sS + 1; s < 16; ++s, pT += 320)
     {
-        const float xT = fadd(C.wT, At[320 * s]);
-        if ((s & 3) == C.c)
+        const float xT = fadd(C.wT, *pT);
+        if (s == so)
         {
-            const float2 o = *reinterpret_cast< const float2* >(Ao + 1280 * (s >> 2));
+            const float2 o = *reinterpret_cast< const float2* >(pO);
+            so += 4;
+            pO += 1280;
             const float xO0 = fadd(C.wO[0], o.x), xO1 = fadd(C.wO[1], o.y);
             const float a0 = oBef0 ? xO0 : (oEq0 ? NI : xT), b0 = oBef0 ? xT : xO0;
             const float a1 = oBef1 ? xO1 : (oEq1 ? NI : xT), b1 = oBef1 ? xT : xO1;
@@ -341,8 +348,9 @@ struct BwdConst
     unsigned smask[2];  // 6-bit self masks of the 8 states: state k at bits 6(k>>1) of smask[k&1]
     unsigned flags;  // bit f: oIn[f] (one-step block inside the two-step block), bit 2+f: oBef[f] (one-step block first),
                      // bits 4+2f..5+2f: c4[f] = position (0..3) of the one-step block inside the two-step block
-    unsigned paths;  // 2 bits per state (warp-uniform): 0 = generic chain, 1 = self after both blocks,
-                     // 2 = self between the blocks, one-step block first, 3 = self between, two-step block first
+    unsigned paths;  // 3 bits per state (warp-uniform): 0 = generic chain, 1 = self after both blocks,
+                     // 2 = self between the blocks, one-step block first, 3 = self between, two-step block first,
+                     // 4 = self before both blocks
 };
 
 // per-lane classification of state k of thread t: the kernel (and the emulation) turn it into `paths` with a vote
@@ -358,7 +366,7 @@ NC_HD unsigned bwd_lane_code(int t, int k)
     const int pos = (j > tb ? 1 : 0) + (j > ob ? 1 : 0);
     if (pos == 2) return 1;
     if (pos == 1) return oBef ? 2 : 3;
-    return 0;
+    return 4;
 }
 
 NC_HD void bwd_const_init(BwdConst& C, int t, const float* __restrict__ lut)
@@ -487,7 +495,7 @@ NC_HD void bwd_column(const BwdConst& C, const float* __restrict__ Bn, const flo
             const float eS = En[j];
 #endif
             const float vS = fadd(fadd(wS, eS), Bn[cphys(j)]);
-            const unsigned path = (C.paths >> (2 * k)) & 3u;
+            const unsigned path = (C.paths >> (3 * k)) & 7u;
             float acc;
             if (path == 1) acc = flogsum(m20, vS, tbl);
             else if (path == 2)
@@ -505,6 +513,14 @@ NC_HD void bwd_column(const BwdConst& C, const float* __restrict__ Bn, const flo
 #pragma unroll
 #endif
                 for (int q = 16; q < 20; ++q) acc = flogsum(acc, L[q], tbl);
+            }
+            else if (path == 4)
+            {
+                acc = vS;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+                for (int q = 0; q < 20; ++q) acc = flogsum(acc, L[q], tbl);
             }
             else
             {

@@ -49,6 +49,12 @@ struct VitArgs
     unsigned* tb_head;          // tickets claimed
     unsigned* slab_free;        // per forward CTA: number of its jobs the traceback service has released
     void* colalloc;             // device-wide allocator of alpha columns (ColAlloc in nc_viterbi_alpha.cu)
+    unsigned* abort_word;       // zeroed before the launch; a CTA that waited longer than the deadline for columns or for a
+                                // ticket (the persistent grid is not making progress), or that found the allocator's
+                                // extent list full, writes a non-zero code here and every waiting loop gives up on seeing it:
+                                // the call then fails with NC_ERR_STATE instead of hanging (1 = wait for a CTA's release slot,
+                                // 2 = wait for columns, 3 = wait for a ticket, 4 = extent list full)
+    long long wait_limit;       // SM cycles a CTA may wait for columns / tickets before it raises abort_word
     unsigned long long* stats;  // optional (may be null): [0] forward cycles, [1] forward cycles waiting for a slab,
                                 // [2] traceback busy cycles, [3] traceback cycles waiting for a ticket, [4] passes,
                                 // [5] lane steps, [6] jobs traced   (sums over CTAs / service warps)
@@ -59,6 +65,7 @@ size_t viterbi_smem_bytes();
 __global__ void viterbi_alpha_kernel(const VitArgs a);  // alpha-column form (fast path: 16 KiB/event of scratch)
 size_t viterbi_alpha_smem_bytes();
 size_t viterbi_alpha_colalloc_bytes();
+unsigned viterbi_alpha_max_forward_ctas();   // bound of the allocator's extent list
 void viterbi_alpha_colalloc_init(void* host_image, unsigned pool_columns);
 
 // ---- Forward/Backward + trainer statistics

@@ -286,6 +286,12 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned ldv_abort(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
 {
     unsigned v;
@@ -293,6 +299,19 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
     return v;
 }
 
+
+// ---------------- liveness guard of the persistent grid.  Forward CTAs wait for columns that the traceback service
+// releases and service warps wait for tickets that forward CTAs publish: both need the whole grid resident (the host
+// launches it cooperatively, which the driver refuses when that is impossible) and making progress.  Every such wait
+// is bounded: after a.wait_limit cycles without progress (two minutes by default; a healthy wait is microseconds) the waiter
+// raises the abort word, every other wait loop sees it and the CTAs drain, and the host reports NC_ERR_STATE.
+__device__ __forceinline__ bool aborted(const VitArgs& a) { return ldv_abort(a.abort_word) != 0u; }
+__device__ __forceinline__ bool give_up(const VitArgs& a, long long t0, unsigned code)
+{
+    if (ldv_abort(a.abort_word) != 0u) return true;
+    if (clock64() - t0 > a.wait_limit) { atomicCAS(a.abort_word, 0u, code); return true; }
+    return false;
+}
 
 // ---------------- device-wide allocator of alpha columns.
 // The scratch pool is P columns of 16 KiB.  A job takes n consecutive columns for the time between the start of its
@@ -373,7 +392,7 @@ __device__ __forceinline__ bool ca_alloc(ColAlloc* A, unsigned n, unsigned& s, i
     ca_unlock(A, lane);
     return found >= 0;
 }
-__device__ __forceinline__ void ca_free(ColAlloc* A, unsigned s, unsigned n, int lane)
+__device__ __forceinline__ void ca_free(ColAlloc* A, unsigned s, unsigned n, int lane, unsigned* abort_word)
 {
     ca_lock(A, lane);
     const unsigned nf = ldv(&A->n_free);
@@ -419,7 +438,8 @@ __device__ __forceinline__ void ca_free(ColAlloc* A, unsigned s, unsigned n, int
         }
         if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, n); stv(&A->n_free, nf + 1); }
     }
-    // (a full list would leak the extent; CA_MAX_LIVE jobs per forward CTA keep it far below CA_MAX)
+    else if (lane == 0) atomicCAS(abort_word, 0u, 4u);   // extent list full: an error, not a silent leak (the host also
+                                                         // refuses launches whose live jobs could exceed the list)
     ca_unlock(A, lane);
 }
 
@@ -467,20 +487,33 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
             {
                 const long long c0 = clock64();
                 unsigned ns = 64;
+                bool gave_up = false;
                 if (lane == 0)
-                    while (ld_acquire_u32(a.slab_free + fwd_id) + CA_MAX_LIVE <= jobs_done) { __nanosleep(ns); if (ns < 4096) ns *= 2; }
-                __syncwarp();
+                    while (ld_acquire_u32(a.slab_free + fwd_id) + CA_MAX_LIVE <= jobs_done)
+                    {
+                        if (give_up(a, c0, 1u)) { gave_up = true; break; }
+                        __nanosleep(ns);
+                        if (ns < 4096) ns *= 2;
+                    }
+                gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
                 unsigned got = 0;
                 ns = 128;
-                while (!ca_alloc(CA, n, got, lane)) { __nanosleep(ns); if (ns < 8192) ns *= 2; }
+                while (!gave_up && !ca_alloc(CA, n, got, lane))
+                {
+                    if (give_up(a, c0, 2u)) gave_up = true;
+                    gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
+                    __nanosleep(ns);
+                    if (ns < 8192) ns *= 2;
+                }
                 if (lane == 0)
                 {
-                    sm.col0 = got;
+                    sm.col0 = gave_up ? 0xffffffffu : got;
                     if (a.stats) atomicAdd(a.stats + 1, (unsigned long long)(clock64() - c0));
                 }
             }
             __syncthreads();
             col0 = sm.col0;
+            if (col0 == 0xffffffffu) return;   // the grid was aborted: drain (the host reports the failure)
         }
         float* const acol = reinterpret_cast< float* >(a.bp_pool) + (size_t)col0 * NC_N_STATES;
         const long long fwd_c0 = clock64();
@@ -729,12 +762,18 @@ __device__ void traceback_service(const VitArgs& a)
         if (h >= a.n_jobs) return;
         TbTicket& tk = a.tickets[h];
         const long long w0 = clock64();
+        bool gave_up = false;
         if (lane == 0)
         {
             unsigned ns = 64;
-            while (ld_acquire_u32(&tk.ready) == 0u) { __nanosleep(ns); if (ns < 2048) ns *= 2; }
+            while (ld_acquire_u32(&tk.ready) == 0u)
+            {
+                if (give_up(a, w0, 3u)) { gave_up = true; break; }
+                __nanosleep(ns);
+                if (ns < 2048) ns *= 2;
+            }
         }
-        __syncwarp();
+        if (__shfl_sync(0xffffffffu, gave_up, 0)) return;
         const long long w1 = clock64();
         unsigned passes = 0, steps = 0;
         const unsigned job_idx = __ldcg(&tk.job), slab_id = __ldcg(&tk.slab), final_state = __ldcg(&tk.final_state);
@@ -792,7 +831,7 @@ __device__ void traceback_service(const VitArgs& a)
         }
         __threadfence();   // states visible to the lanes that derive the moves; slab reads are complete
         __syncwarp();
-        ca_free(reinterpret_cast< ColAlloc* >(a.colalloc), col0, n, lane);
+        ca_free(reinterpret_cast< ColAlloc* >(a.colalloc), col0, n, lane, a.abort_word);
         if (lane == 0) atomicAdd(a.slab_free + slab_id, 1u);   // slab_id = the forward CTA that ran the job
         if (a.stats)
         {
@@ -827,6 +866,7 @@ __global__ void __launch_bounds__(VIT_THREADS, 1) viterbi_alpha_kernel(const Vit
 
 size_t viterbi_alpha_smem_bytes() { return sizeof(SmemA); }
 size_t viterbi_alpha_colalloc_bytes() { return sizeof(ColAlloc); }
+unsigned viterbi_alpha_max_forward_ctas() { return (CA_MAX - 1) / CA_MAX_LIVE; }   // live extents + 1 free extents <= CA_MAX
 void viterbi_alpha_colalloc_init(void* host_image, unsigned pool_columns)
 {
     ColAlloc* A = static_cast< ColAlloc* >(host_image);

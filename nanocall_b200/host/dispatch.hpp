@@ -35,7 +35,7 @@ struct Device_Stats
     size_t reads = 0, batches = 0, train_rounds = 0, fwbw_events = 0, viterbi_events = 0, read_events = 0;
     double train_kernel_ms = 0, viterbi_kernel_ms = 0;
     double emission_ms = 0, fwbw_ms = 0, pm_stats_ms = 0, st_stats_ms = 0;
-    double init_s = 0, train_s = 0, basecall_s = 0, wait_s = 0;
+    double init_s = 0, train_s = 0, basecall_s = 0, wait_s = 0, train_call_s = 0, viterbi_call_s = 0;
     double first_batch_at_s = 0, last_batch_done_s = 0;   // relative to the start of the run
 };
 

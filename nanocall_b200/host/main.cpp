@@ -286,7 +286,8 @@ int main(int argc, char** argv)
         s << "gpu " << d.device << ": reads=" << d.reads << " batches=" << d.batches << " train_rounds=" << d.train_rounds
           << " fwbw_events=" << d.fwbw_events << " train_kernel_ms=" << d.train_kernel_ms << " viterbi_events=" << d.viterbi_events
           << " viterbi_kernel_ms=" << d.viterbi_kernel_ms << " init_s=" << d.init_s << " train_s=" << d.train_s
-          << " basecall_s=" << d.basecall_s << " wait_s=" << d.wait_s << " emission_ms=" << d.emission_ms << " fwbw_ms=" << d.fwbw_ms
+          << " basecall_s=" << d.basecall_s << " train_call_s=" << d.train_call_s << " viterbi_call_s=" << d.viterbi_call_s
+          << " wait_s=" << d.wait_s << " emission_ms=" << d.emission_ms << " fwbw_ms=" << d.fwbw_ms
           << " pm_stats_ms=" << d.pm_stats_ms << " st_stats_ms=" << d.st_stats_ms;
         log_line(2, lvl, s.str());
     }

@@ -4,6 +4,7 @@
 #include "pipeline.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -360,9 +361,11 @@ void Pipeline::train_reads(std::vector< Read* >& reads)
             tin[a].st[0] = c.crt_st[0];
             tin[a].st[1] = c.crt_st[1];
         }
+        const auto c0 = std::chrono::steady_clock::now();
         check(nc_train_round_batch(ctx_, (uint32_t)act.size(), seq_off.data(), ev_off.data(), strands.data(),
                                    mean.data(), stdv.data(), start.data(), tin.data(), &topts, tout.data()),
               "nc_train_round_batch");
+        train_call_s += std::chrono::duration< double >(std::chrono::steady_clock::now() - c0).count();
         train_kernel_ms += nc_ctx_last_kernel_ms(ctx_);
         ++train_rounds;
         fwbw_events += ev_off.back();
@@ -529,9 +532,11 @@ void Pipeline::basecall_reads(std::vector< Read* >& reads)
         std::vector< uint8_t > moves(off.back());
         if (nj)
         {
+            const auto c0 = std::chrono::steady_clock::now();
             check(nc_viterbi_packed(ctx_, nj, off.data(), mean.data(), stdv.data(), start.data(), nullptr, mid.data(),
                                     pm.data(), st.data(), NC_MEM_HOST, path.data(), states.data(), moves.data()),
                   "nc_viterbi_packed");
+            viterbi_call_s += std::chrono::duration< double >(std::chrono::steady_clock::now() - c0).count();
             viterbi_kernel_ms += nc_ctx_last_kernel_ms(ctx_);
             viterbi_events += off.back();
         }

@@ -113,6 +113,7 @@ public:
     nc_ctx* ctx() { return ctx_; }
     // device time spent in the hot-path kernels (ms), for the run summary
     double train_kernel_ms = 0, viterbi_kernel_ms = 0;
+    double train_call_s = 0, viterbi_call_s = 0;   // wall time inside the two C-ABI calls (copies included)
     size_t train_rounds = 0, fwbw_events = 0, viterbi_events = 0;
 
 private:

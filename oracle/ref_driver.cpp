@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include <array>
@@ -293,11 +294,15 @@ int ncref_train_one_round(unsigned n_seqs, const uint32_t* seq_len, const uint32
 {
     static ST default_transitions;
     static float def_key[2] = { -1, -1 };
-    if (def_key[0] != STP::default_p_stay() or def_key[1] != STP::default_p_skip())
+    static std::mutex def_mutex;   // bench.py times this entry point from several threads
     {
-        default_transitions.compute_transitions_fast(STP::default_p_skip(), STP::default_p_stay());
-        def_key[0] = STP::default_p_stay();
-        def_key[1] = STP::default_p_skip();
+        std::lock_guard< std::mutex > def_lock(def_mutex);
+        if (def_key[0] != STP::default_p_stay() or def_key[1] != STP::default_p_skip())
+        {
+            default_transitions.compute_transitions_fast(STP::default_p_skip(), STP::default_p_stay());
+            def_key[0] = STP::default_p_stay();
+            def_key[1] = STP::default_p_skip();
+        }
     }
     PM m0 = make_model(table0);
     PM m1 = make_model(table1);

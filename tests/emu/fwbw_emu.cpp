@@ -66,7 +66,7 @@ int emu_backward(const float* lut, const float* tbl, const float* E, uint32_t n,
             for (int l = 1; l < 32; ++l) all = all && bwd_lane_code(32 * w + l, k) == c0;
             const unsigned path = all ? c0 : 0u;
             if (path_hist) ++path_hist[path];
-            for (int l = 0; l < 32; ++l) C[32 * w + l].paths |= path << (2 * k);
+            for (int l = 0; l < 32; ++l) C[32 * w + l].paths |= path << (3 * k);
         }
     for (int j = 0; j < N_STATES; ++j) { col[0][cphys(j)] = 0.f; beta[(size_t)(n - 1) * N_STATES + j] = 0.f; }
     int cur = 0;

@@ -68,10 +68,10 @@ def test_emulated_kernel_columns_match_oracle(emu, port, models, st):
     n = E.shape[0]
     alpha = np.zeros((n, 4096), np.float32)
     beta = np.zeros((n, 4096), np.float32)
-    hist = np.zeros(4, np.uint32)
+    hist = np.zeros(8, np.uint32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     assert emu.emu_forward(p(lut), p(tbl), p(E), n, C.c_float(np.log(np.float32(4096))), p(alpha)) == 0
     assert emu.emu_backward(p(lut), p(tbl), p(E), n, p(beta), p(hist)) == 0
     assert np.array_equal(alpha.view(np.uint32), exp["alpha"].view(np.uint32)), np.argwhere(alpha != exp["alpha"])[:5]
     assert np.array_equal(beta.view(np.uint32), exp["beta"].view(np.uint32)), np.argwhere(beta != exp["beta"])[:5]
-    assert hist.sum() == 16 * 8 and hist[0] < 70   # most (warp, state) pairs take a shared-prefix path
+    assert hist.sum() == 16 * 8 and hist[0] < 40   # most (warp, state) pairs take a shared-prefix path

@@ -100,10 +100,14 @@ def test_single_strand_and_no_train(tmp_path, port, models):
         for st, call in exp["calls"].items():
             assert fa[f"{rid}:batch:{st}"] == call["bases"], (rid, st)
         assert (f"{rid}:batch:1" in fa) == (1 in exp["calls"])
-    # --no-train: initial scaling only, every applicable model scored by Viterbi, best path probability wins
+    # --no-train: initial scaling only, every applicable model scored by Viterbi, best path probability wins.  Without
+    # training --double-strand-scaling is NOT the default (nanocall.cpp:1012-1026 sets it only when scaling is trained):
+    # the strands are scaled and ranked separately (confirmed by the reference program itself, ref_r73_notrain golden)
     fa2, stderr2, _ = _run_cli(str(tmp_path), reads[:2], ["--no-train"])
+    nt_opts = OP.Opts()
+    nt_opts.double_strand_scaling = False
     for rid, ev in reads[:2]:
-        exp = OP.run_read(port, mdl, ev, OP.Opts(), train=False)
+        exp = OP.run_read(port, mdl, ev, nt_opts, train=False)
         for st, call in exp["calls"].items():
             assert fa2[f"{rid}:batch:{st}"] == call["bases"], (rid, st)
             assert f"best_model read [{rid}] strand [{st}] model [{call['model']}]" in stderr2
@@ -127,7 +131,9 @@ def test_events_tsv_input(tmp_path, port, models):
     p = subprocess.run([CLI, "--pore", "r73", "--no-train", "-o", out, "--log", "warning", str(tmp_path)],
                        capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr
-    exp = OP.run_read(port, mdl, rd[1], OP.Opts(), train=False)
+    nt_opts = OP.Opts()
+    nt_opts.double_strand_scaling = False   # --no-train: strands are scaled separately (nanocall.cpp:1012-1026)
+    exp = OP.run_read(port, mdl, rd[1], nt_opts, train=False)
     text = open(out).read().split("\n")
     assert text[0] == ">tsvread:one:0"
     seqs = "".join(text).split(">")

@@ -278,3 +278,71 @@ def test_path_probability_only_needs_no_scratch(port, models, vit_mode):
         assert np.array_equal(_bits(out["path_logprob"]), _bits(exp["path_prob"]))
     finally:
         c.close()
+
+
+def test_two_contexts_one_thread_and_concurrent_training(port, models, vit_mode):
+    """Two contexts driven from one host thread (every entry point selects its own device), and the alpha-column
+    kernel's persistent grid running while another context's Forward/Backward kernels occupy SMs: the grid is
+    launched cooperatively, so it waits for the SMs it needs instead of deadlocking on half-resident CTAs."""
+    if vit_mode != "alpha":
+        pytest.skip("runs once")
+    import threading
+    table = models[R73T]["table"]
+    a, b = api.Context(0, bp_pool_bytes=4 << 30), api.Context(0, bp_pool_bytes=4 << 30)
+    try:
+        ma, mb = a.register_model(table, 0), b.register_model(table, 0)
+        batch = synth.make_batch(61, table, [3000, 500, 1800, 2500] * 40)
+        rng = np.random.default_rng(5)
+        groups = []
+        for k in range(64):
+            rd = synth.make_read(rng, table, 200)
+            seqs = [(0, rd["mean"][:100], rd["stdv"][:100], rd["start"][:100]), (0, rd["mean"][100:], rd["stdv"][100:], rd["start"][100:])]
+            groups.append(dict(seqs=seqs, model_id=(mb, mb), pm=(1, 0, 0, 1, 1, 1), st=(0.1, 0.3, 0.1, 0.3)))
+        # interleaved calls from ONE thread
+        first = b.train_round_batch(groups[:4])
+        _check_batch(a, port, table, ma, batch, None, None)
+        again = b.train_round_batch(groups[:4])
+        assert all(np.array_equal(x["pm"].view(np.uint32), y["pm"].view(np.uint32)) for x, y in zip(first, again))
+        # training on context b in a second thread while context a decodes
+        stop = threading.Event()
+        errs = []
+
+        def train_loop():
+            try:
+                while not stop.is_set():
+                    b.train_round_batch(groups)
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        th = threading.Thread(target=train_loop)
+        th.start()
+        try:
+            for _ in range(3):
+                _check_batch(a, port, table, ma, batch, None, None)
+        finally:
+            stop.set()
+            th.join()
+        assert not errs, errs
+    finally:
+        a.close()
+        b.close()
+
+
+def test_stalled_grid_is_an_error_not_a_hang(models, vit_mode, monkeypatch):
+    """A pool too small for the first wave of jobs plus a wait limit of a few milliseconds: forward CTAs cannot get
+    columns in time, the grid drains and the call fails with NC_ERR_STATE (or succeeds if the hardware was quick) --
+    it never hangs."""
+    if vit_mode != "alpha":
+        pytest.skip("runs once")
+    monkeypatch.setenv("NC_WAIT_LIMIT_S", "0.002")
+    from nanocall_b200 import _lib as L
+    table = models[R73T]["table"]
+    c = api.Context(0, bp_pool_bytes=200 << 20)   # 12800 columns for ~300 jobs of 6000 events
+    try:
+        mid = c.register_model(table, 0)
+        batch = synth.make_batch(71, table, [6000] * 300)
+        try:
+            c.viterbi(batch["ev_off"], batch["mean"], batch["stdv"], batch["start"], mid)
+        except api.NanocallError as e:
+            assert e.code == L.NC_ERR_STATE and "alpha-column kernel stopped" in str(e)
+    finally:
+        c.close()
