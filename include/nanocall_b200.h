@@ -162,6 +162,12 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
                          const float* mean, const float* stdv, const float* start,
                          const nc_train_in* in, const nc_train_opts* opts, nc_train_out* out);
 
+/* Page-locked host memory for the event / state / move arrays of NC_MEM_HOST calls.  Optional: any host memory works,
+ * but only pinned buffers are copied at full PCIe rate and let nc_viterbi_packed stream the events behind the kernel
+ * launch.  nc_host_alloc returns NULL when the allocation fails (or there is no CUDA device). */
+void* nc_host_alloc(size_t bytes);
+void nc_host_free(void* p);
+
 /* Device time of the training kernels since the last reset (CUDA events on the context's stream, summed over the waves
  * of every nc_train_round_batch / nc_fwbw call): out8 = { emission_kernel ms, fwbw_kernel ms, pm_stats_kernel ms,
  * st_stats_kernel ms, Forward/Backward events processed, kernels launched, waves, 0 }. */

@@ -394,7 +394,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     a.colalloc = nullptr;
     a.stats = ctx->d_stats;
     a.abort_word = ctx->d_abort;
-    a.wait_limit = (long long)(ctx->wait_limit_s * 1e3 * (double)ctx->prop.clockRate);   // clockRate is in kHz
+    a.wait_limit = (long long)(ctx->wait_limit_s * 1e9);   // nanoseconds of back-off
     NC_CUDA_INFLIGHT(cudaMemsetAsync(ctx->d_abort, 0, sizeof(unsigned), s));
 
     a.landed = nullptr;
@@ -530,12 +530,39 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         static const char* const why[] = { "", "a forward CTA waited for its release slot", "a forward CTA waited for alpha columns",
                                            "a traceback warp waited for a ticket", "the column allocator's extent list overflowed" };
         const unsigned code = *ctx->h_abort;
+        // what the grid looked like when it gave up: jobs started / finished / claimed by the traceback service, and the
+        // column allocator's free list
+        char diag[256] = "";
+        if (n_short && want_path)
+        {
+            std::vector< unsigned char > img(ca_bytes);
+            unsigned ctl[2] = { 0, 0 }, started[2] = { 0, 0 };
+            cudaMemcpy(img.data(), (char*)ctx->tb.p + tk_bytes + ctl_bytes, ca_bytes, cudaMemcpyDeviceToHost);
+            cudaMemcpy(ctl, (char*)ctx->tb.p + tk_bytes, sizeof ctl, cudaMemcpyDeviceToHost);
+            cudaMemcpy(started, ctx->counter.p, sizeof started, cudaMemcpyDeviceToHost);
+            const unsigned* w = reinterpret_cast< const unsigned* >(img.data());   // lock, n_free, pad[2], start[], len[]
+            const unsigned nf = std::min(w[1], 1024u);
+            unsigned long long free_cols = 0;
+            unsigned largest = 0;
+            for (unsigned k = 0; k < nf; ++k) { free_cols += w[4 + 1024 + k]; largest = std::max(largest, w[4 + 1024 + k]); }
+            std::snprintf(diag, sizeof diag, "; alpha jobs %u (longest %u events), started %u, finished %u, claimed by the traceback service %u; "
+                          "pool %zu columns, free %llu in %u extents (largest %u), lock %u", n_short, jobs[order[n_long]].n_events,
+                          started[1], ctl[0], ctl[1], slab_a / a_col, free_cols, nf, largest, w[0]);
+        }
         NC_FAIL(ctx, NC_ERR_STATE, "nc_viterbi_packed: the alpha-column kernel stopped without finishing (%s for more than %.0f s): "
-                "results of this call are invalid", code < 5 ? why[code] : "unknown reason", ctx->wait_limit_s);
+                "results of this call are invalid%s", code < 5 ? why[code] : "unknown reason", ctx->wait_limit_s, diag);
     }
     return NC_OK;
 #undef NC_CUDA_INFLIGHT
 }
+
+void* nc_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void nc_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int nc_viterbi_batch(nc_ctx* ctx, uint32_t n_jobs, const nc_vit_job* jobs, nc_vit_out* outs)
 {

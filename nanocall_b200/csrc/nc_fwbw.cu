@@ -371,9 +371,30 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
         // ---- producers: thread p handles state jt*52 + (p % 52) for the events (p / 52) and (p / 52) + 8
         const int p = t - PM_CHAINS;
         const int jl = p % PM_JT, eg = p / PM_JT;   // eg = 0..7
+        // alpha + beta of the NEXT tile are loaded while the current one is computed (the loads come from HBM: every
+        // tile touches a new 208-byte piece of each of the 16 event rows)
+        float al[2], be[2];
+        auto load_tile = [&](int tile, float (&a2)[2], float (&b2)[2]) {
+            const int j = tile * PM_JT + jl;
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+            {
+                const unsigned ev = (unsigned)(eg + 8 * r);
+                a2[r] = b2[r] = 0.f;
+                if (tile < PM_TILES && j < (int)NC_N_STATES && ev < n_ev)
+                {
+                    const size_t o = (size_t)(i0 + ev) * NC_N_STATES + j;
+                    a2[r] = __ldcs(AL + o);
+                    b2[r] = __ldcs(BE + o);
+                }
+            }
+        };
+        load_tile(0, al, be);
         for (int tile = 0; tile < PM_TILES; ++tile)
         {
             const int j = tile * PM_JT + jl;
+            float aln[2], ben[2];
+            load_tile(tile + 1, aln, ben);
             float* T = term + (size_t)(tile & 1) * PM_JT * PM_ROW + jl * PM_ROW;
             if (j < (int)NC_N_STATES)
             {
@@ -390,11 +411,10 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
                     float ts0 = 0.f, ts1 = 0.f, ts2 = 0.f, tl0 = 0.f, tl1 = 0.f, tl2 = 0.f;
                     if (ev < n_ev)
                     {
-                        const size_t o = (size_t)(i0 + ev) * NC_N_STATES + j;
                         // the posterior, scaled by 2^64 (exact): every term below stays in the normal range, so the
                         // correctly rounded divisions are three instructions (div_rn) instead of the IEEE division's
                         // denormal slow path, which two thirds of the kernel's instructions used to be
-                        const float pst = __fmul_rn(nc_expf(__fsub_rn(__fadd_rn(__ldcs(AL + o), __ldcs(BE + o)), logz)), PM_SCALE);
+                        const float pst = __fmul_rn(nc_expf(__fsub_rn(__fadd_rn(al[r], be[r]), logz)), PM_SCALE);
                         ts0 = div_rn(pst, sg2, rsg2);
                         ts1 = __fmul_rn(ts0, mu);
                         ts2 = __fmul_rn(ts1, mu);
@@ -407,6 +427,7 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
                 }
             }
             __syncthreads();   // publishes tile `tile`; the folding lanes are at most one tile behind
+            al[0] = aln[0]; al[1] = aln[1]; be[0] = ben[0]; be[1] = ben[1];
         }
     }
 }

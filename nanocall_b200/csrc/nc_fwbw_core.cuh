@@ -140,6 +140,47 @@ NC_HD float flogsum(float a, float b, const TB& tbl)
     return fadd(mx, tbl(d));
 }
 
+// N independent p7_FLogsum folds written stage by stage (all differences, all maxima, all table addresses, all loads,
+// all sums): the chains of a column are long dependent sequences, and issued one after the other each fold costs its
+// full latency (~50 cycles: four ALU steps, a shared-memory load, an add); interleaved, N folds cost little more than
+// one.  Same operations on the same operands as N calls of flogsum.
+template < int N, typename TB >
+NC_HD void flogsum_n(float (&acc)[N], const float (&x)[N], const TB& tbl)
+{
+    float d[N], mx[N];
+    unsigned ad[N];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < N; ++k) d[k] = fabsf(fsub(acc[k], x[k]));
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < N; ++k) mx[k] = fmaxf(acc[k], x[k]);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < N; ++k) ad[k] = tbl.addr(d[k]);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < N; ++k) d[k] = tbl.load(ad[k]);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < N; ++k) acc[k] = fadd(mx[k], d[k]);
+}
+template < int N, typename TB >
+NC_HD void flogsum_n(float (&acc)[N], const float x, const TB& tbl)
+{
+    float xs[N];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < N; ++k) xs[k] = x;
+    flogsum_n< N >(acc, xs, tbl);
+}
+
 // 6-bit overlap mask of an edge i -> j (State_Transitions::get_trans_prob, State_Transitions.hpp:128-141)
 NC_HD unsigned tmask(unsigned i, unsigned j)
 {
@@ -229,7 +270,7 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
     const float* pT = A + C.offT;   // T_s, advanced by 320 floats per slot
     const float* pO = A + C.offO;   // the O pair of the next one-step slot, advanced by 1280 floats per such slot
     int so = C.c;                   // the next one-step slot
-    float P0 = NI, P1 = NI;
+    float P[2] = { NI, NI };
     // ---- slots below the self slot: one chain per half
     for (int s = 0; s < C.sS; ++s, pT += 320)
     {
@@ -242,14 +283,11 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
             const float xO0 = fadd(C.wO[0], o.x), xO1 = fadd(C.wO[1], o.y);
             const float a0 = oBef0 ? xO0 : (oEq0 ? NI : xT), b0 = oBef0 ? xT : xO0;
             const float a1 = oBef1 ? xO1 : (oEq1 ? NI : xT), b1 = oBef1 ? xT : xO1;
-            P0 = flogsum(flogsum(P0, a0, tbl), b0, tbl);
-            P1 = flogsum(flogsum(P1, a1, tbl), b1, tbl);
+            const float xa[2] = { a0, a1 }, xb[2] = { b0, b1 };
+            flogsum_n< 2 >(P, xa, tbl);
+            flogsum_n< 2 >(P, xb, tbl);
         }
-        else
-        {
-            P0 = flogsum(P0, xT, tbl);
-            P1 = flogsum(P1, xT, tbl);
-        }
+        else flogsum_n< 2 >(P, xT, tbl);
     }
     // ---- the self slot: per state
     float acc[8];
@@ -263,6 +301,7 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
             so += 4;
             pO += 1280;
             const float xO0 = fadd(C.wO[0], o.x), xO1 = fadd(C.wO[1], o.y);
+            float f0[8], f1[8], f2[8], f3[8], f4[8];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
@@ -273,20 +312,24 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
                 const bool sEqT = (F >> (16 + k)) & 1u, sEqO = (F >> (24 + k)) & 1u;
                 const float xO = sEqO ? NI : (h ? xO1 : xO0);
                 const float xTd = (oEq || sEqT) ? NI : xT;
-                const float first = oBef ? xO : xTd, second = oBef ? xTd : xO;
                 const unsigned p = (C.pos >> (2 * k)) & 3u;
                 const float vS = fadd(C.wS[k], own[k]);
-                float a = h ? P1 : P0;
-                a = flogsum(a, p == 0 ? vS : NI, tbl);
-                a = flogsum(a, first, tbl);
-                a = flogsum(a, p == 1 ? vS : NI, tbl);
-                a = flogsum(a, second, tbl);
-                a = flogsum(a, p == 2 ? vS : NI, tbl);
-                acc[k] = a;
+                f0[k] = p == 0 ? vS : NI;
+                f1[k] = oBef ? xO : xTd;
+                f2[k] = p == 1 ? vS : NI;
+                f3[k] = oBef ? xTd : xO;
+                f4[k] = p == 2 ? vS : NI;
+                acc[k] = P[h];
             }
+            flogsum_n< 8 >(acc, f0, tbl);
+            flogsum_n< 8 >(acc, f1, tbl);
+            flogsum_n< 8 >(acc, f2, tbl);
+            flogsum_n< 8 >(acc, f3, tbl);
+            flogsum_n< 8 >(acc, f4, tbl);
         }
         else
         {
+            float e1[8], e2[8];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
@@ -294,10 +337,12 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
             {
                 const bool sFirst = (F >> (8 + k)) & 1u, sEq = (F >> (16 + k)) & 1u;
                 const float vS = fadd(C.wS[k], own[k]);
-                const float e1 = (sFirst || sEq) ? vS : xT;
-                const float e2 = sEq ? NI : (sFirst ? xT : vS);
-                acc[k] = flogsum(flogsum((k >> 2) ? P1 : P0, e1, tbl), e2, tbl);
+                e1[k] = (sFirst || sEq) ? vS : xT;
+                e2[k] = sEq ? NI : (sFirst ? xT : vS);
+                acc[k] = P[k >> 2];
             }
+            flogsum_n< 8 >(acc, e1, tbl);
+            flogsum_n< 8 >(acc, e2, tbl);
         }
     }
     // ---- slots above the self slot: per state
@@ -312,22 +357,11 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
             const float xO0 = fadd(C.wO[0], o.x), xO1 = fadd(C.wO[1], o.y);
             const float a0 = oBef0 ? xO0 : (oEq0 ? NI : xT), b0 = oBef0 ? xT : xO0;
             const float a1 = oBef1 ? xO1 : (oEq1 ? NI : xT), b1 = oBef1 ? xT : xO1;
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-            for (int k = 0; k < 4; ++k) acc[k] = flogsum(flogsum(acc[k], a0, tbl), b0, tbl);
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-            for (int k = 4; k < 8; ++k) acc[k] = flogsum(flogsum(acc[k], a1, tbl), b1, tbl);
+            const float xa[8] = { a0, a0, a0, a0, a1, a1, a1, a1 }, xb[8] = { b0, b0, b0, b0, b1, b1, b1, b1 };
+            flogsum_n< 8 >(acc, xa, tbl);
+            flogsum_n< 8 >(acc, xb, tbl);
         }
-        else
-        {
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-            for (int k = 0; k < 8; ++k) acc[k] = flogsum(acc[k], xT, tbl);
-        }
+        else flogsum_n< 8 >(acc, xT, tbl);
     }
 #ifdef __CUDA_ARCH__
 #pragma unroll

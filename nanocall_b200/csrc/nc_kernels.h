@@ -54,7 +54,8 @@ struct VitArgs
                                 // extent list full, writes a non-zero code here and every waiting loop gives up on seeing it:
                                 // the call then fails with NC_ERR_STATE instead of hanging (1 = wait for a CTA's release slot,
                                 // 2 = wait for columns, 3 = wait for a ticket, 4 = extent list full)
-    long long wait_limit;       // SM cycles a CTA may wait for columns / tickets before it raises abort_word
+    long long wait_limit;       // nanoseconds of polling back-off a CTA may spend waiting for columns / tickets before it
+                                // raises abort_word
     unsigned long long* stats;  // optional (may be null): [0] forward cycles, [1] forward cycles waiting for a slab,
                                 // [2] traceback busy cycles, [3] traceback cycles waiting for a ticket, [4] passes,
                                 // [5] lane steps, [6] jobs traced   (sums over CTAs / service warps)

@@ -303,13 +303,15 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
 // ---------------- liveness guard of the persistent grid.  Forward CTAs wait for columns that the traceback service
 // releases and service warps wait for tickets that forward CTAs publish: both need the whole grid resident (the host
 // launches it cooperatively, which the driver refuses when that is impossible) and making progress.  Every such wait
-// is bounded: after a.wait_limit cycles without progress (two minutes by default; a healthy wait is microseconds) the waiter
+// is bounded: after a.wait_limit nanoseconds of back-off without progress (two minutes by default; a healthy wait is microseconds) the waiter
 // raises the abort word, every other wait loop sees it and the CTAs drain, and the host reports NC_ERR_STATE.
 __device__ __forceinline__ bool aborted(const VitArgs& a) { return ldv_abort(a.abort_word) != 0u; }
-__device__ __forceinline__ bool give_up(const VitArgs& a, long long t0, unsigned code)
+// slept = nanoseconds this wait has asked __nanosleep for so far (the waiters back off to a few microseconds per poll, so
+// the sum tracks the elapsed time from below; SM cycle counters turned out not to be a reliable clock for this)
+__device__ __forceinline__ bool give_up(const VitArgs& a, unsigned long long slept, unsigned code)
 {
     if (ldv_abort(a.abort_word) != 0u) return true;
-    if (clock64() - t0 > a.wait_limit) { atomicCAS(a.abort_word, 0u, code); return true; }
+    if (slept > (unsigned long long)a.wait_limit) { atomicCAS(a.abort_word, 0u, code); return true; }
     return false;
 }
 
@@ -487,22 +489,26 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
             {
                 const long long c0 = clock64();
                 unsigned ns = 64;
+                unsigned long long slept = 0;
                 bool gave_up = false;
                 if (lane == 0)
                     while (ld_acquire_u32(a.slab_free + fwd_id) + CA_MAX_LIVE <= jobs_done)
                     {
-                        if (give_up(a, c0, 1u)) { gave_up = true; break; }
+                        if (give_up(a, slept, 1u)) { gave_up = true; break; }
                         __nanosleep(ns);
+                        slept += ns;
                         if (ns < 4096) ns *= 2;
                     }
                 gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
                 unsigned got = 0;
                 ns = 128;
+                slept = 0;
                 while (!gave_up && !ca_alloc(CA, n, got, lane))
                 {
-                    if (give_up(a, c0, 2u)) gave_up = true;
+                    if (give_up(a, slept, 2u)) gave_up = true;
                     gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
                     __nanosleep(ns);
+                    slept += ns;
                     if (ns < 8192) ns *= 2;
                 }
                 if (lane == 0)
@@ -766,10 +772,12 @@ __device__ void traceback_service(const VitArgs& a)
         if (lane == 0)
         {
             unsigned ns = 64;
+            unsigned long long slept = 0;
             while (ld_acquire_u32(&tk.ready) == 0u)
             {
-                if (give_up(a, w0, 3u)) { gave_up = true; break; }
+                if (give_up(a, slept, 3u)) { gave_up = true; break; }
                 __nanosleep(ns);
+                slept += ns;
                 if (ns < 2048) ns *= 2;
             }
         }

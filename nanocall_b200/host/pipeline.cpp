@@ -15,6 +15,7 @@
 #include <limits>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 
 namespace nchost {
 
@@ -458,15 +459,44 @@ struct VitJob
 };
 } // namespace
 
+void* Pipeline::Pinned::reserve(size_t bytes)
+{
+    if (bytes <= cap) return p;
+    if (p) nc_host_free(p);
+    cap = bytes + bytes / 4 + 4096;
+    p = nc_host_alloc(cap);
+    if (!p) { cap = 0; throw std::runtime_error("nc_host_alloc failed"); }
+    return p;
+}
+Pipeline::Pinned::~Pinned() { if (p) nc_host_free(p); }
+
+namespace {
+// fn(i) for i in [0, n) on up to n_threads threads (contiguous ranges; fn must not throw)
+template < typename Fn >
+void parallel_for(size_t n, unsigned n_threads, Fn fn)
+{
+    n_threads = (unsigned)std::min< size_t >(n_threads, (n + 63) / 64);
+    if (n_threads <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+    std::vector< std::thread > th;
+    for (unsigned t = 0; t < n_threads; ++t)
+        th.emplace_back([&, t] {
+            const size_t a = n * t / n_threads, b = n * (t + 1) / n_threads;
+            for (size_t i = a; i < b; ++i) fn(i);
+        });
+    for (auto& x : th) x.join();
+}
+} // namespace
+
 void Pipeline::basecall_reads(std::vector< Read* >& reads)
 {
     const uint64_t max_events_per_call = 48ull << 20;
     size_t r0 = 0;
     while (r0 < reads.size())
     {
+        // ---- pass 1 (serial, light): the jobs of the call = the (read, strand, candidate model) triples the reference's
+        // lambda iterates (:692-733, :787-818), in its order
         std::vector< VitJob > jobs;
         std::vector< uint64_t > off(1, 0);
-        std::vector< float > mean, stdv, start;
         std::vector< int32_t > mid;
         std::vector< nc_pm_params > pm;
         std::vector< nc_st_params > st;
@@ -476,32 +506,25 @@ void Pipeline::basecall_reads(std::vector< Read* >& reads)
             Read& rd = *reads[r1];
             auto add_job = [&](unsigned s, const Model_Key& key, size_t cand) {
                 const Strand_Events& ev = rd.events[s];
+                if (ev.size() == 0) return;   // (the reference would index an empty sequence: Viterbi.hpp:60)
                 const Model& m = models_.at(key[s]);
                 const nc_pm_params& p = rd.pm_params_m.at(key);
                 const nc_st_params& t = rd.st_params_m.at(key)[s];
                 NLOG(2, "basecalling read [" << rd.read_id << "] strand [" << s << "] model [" << key[s]
                             << "] pm_params [" << p << "] st_params [" << t << "]");
-                // means_apart check (:633-683): mean of the scaled model's level means vs mean of the events
-                {
-                    std::vector< float > lv(NC_N_STATES);
-                    for (unsigned j = 0; j < NC_N_STATES; ++j) lv[j] = m.table[4 * j] * p.scale + p.shift;
-                    float mm, ms, em, es;
-                    nc_mean_stdv(NC_N_STATES, lv.data(), &mm, &ms);
-                    nc_mean_stdv((uint32_t)ev.size(), ev.mean.data(), &em, &es);
-                    if (std::abs(em - mm) > 5.0)
-                        NLOG(1, "means_apart read [" << rd.read_id << "] strand [" << s << "] model [" << key[s]
-                                    << "] parameters [" << p << "] model_mean=[" << mm << "] events_mean=[" << em << "]");
-                }
                 jobs.push_back(VitJob{ r1, s, key, cand });
-                mean.insert(mean.end(), ev.mean.begin(), ev.mean.end());
-                stdv.insert(stdv.end(), ev.stdv.begin(), ev.stdv.end());
-                start.insert(start.end(), ev.start.begin(), ev.start.end());
                 off.push_back(off.back() + ev.size());
                 mid.push_back(m.id);
                 pm.push_back(p);
                 st.push_back(t);
             };
-            if (rd.scale_strands_together)
+            if (rd.scale_strands_together && (rd.events[0].size() == 0 || rd.events[1].size() == 0))
+            {
+                // every event of a strand was filtered out after the read was put on the joint path: the reference
+                // would run Viterbi on an empty sequence (undefined); the read is not called
+                NLOG(1, "empty_strand read [" << rd.read_id << "]: not basecalled");
+            }
+            else if (rd.scale_strands_together)
             {
                 std::vector< Model_Key > sub;  // :697-709
                 if (!rd.preferred_model[2][0].empty()) sub.push_back(rd.preferred_model[2]);
@@ -527,39 +550,77 @@ void Pipeline::basecall_reads(std::vector< Read* >& reads)
             ++r1;
         }
         const uint32_t nj = (uint32_t)jobs.size();
+        const size_t total = off.back();
         std::vector< float > path(nj);
-        std::vector< uint16_t > states(off.back());
-        std::vector< uint8_t > moves(off.back());
+        float* mean = static_cast< float* >(pin_mean_.reserve(total * sizeof(float)));
+        float* stdv = static_cast< float* >(pin_stdv_.reserve(total * sizeof(float)));
+        float* start = static_cast< float* >(pin_start_.reserve(total * sizeof(float)));
+        uint16_t* states = static_cast< uint16_t* >(pin_states_.reserve(total * sizeof(uint16_t)));
+        uint8_t* moves = static_cast< uint8_t* >(pin_moves_.reserve(total));
+        // ---- pass 2 (parallel over jobs): events into the pinned staging arrays; the means_apart check (:633-683):
+        // mean of the scaled model's level means against the mean of the events
+        std::vector< std::string > warn(nj);
+        parallel_for(nj, opt_.host_threads, [&](size_t j) {
+            const VitJob& vj = jobs[j];
+            const Read& rd = *reads[vj.read];
+            const Strand_Events& ev = rd.events[vj.strand];
+            std::memcpy(mean + off[j], ev.mean.data(), ev.size() * sizeof(float));
+            std::memcpy(stdv + off[j], ev.stdv.data(), ev.size() * sizeof(float));
+            std::memcpy(start + off[j], ev.start.data(), ev.size() * sizeof(float));
+            const Model& m = models_.at(vj.key[vj.strand]);
+            const nc_pm_params& p = pm[j];
+            float lv[NC_N_STATES];
+            for (unsigned k = 0; k < NC_N_STATES; ++k) lv[k] = m.table[4 * k] * p.scale + p.shift;
+            float mm, ms, em, es;
+            nc_mean_stdv(NC_N_STATES, lv, &mm, &ms);
+            nc_mean_stdv((uint32_t)ev.size(), ev.mean.data(), &em, &es);
+            if (std::abs(em - mm) > 5.0 && opt_.log_level >= 1)
+            {
+                std::ostringstream o;
+                o << "means_apart read [" << rd.read_id << "] strand [" << vj.strand << "] model [" << vj.key[vj.strand]
+                  << "] parameters [" << p << "] model_mean=[" << mm << "] events_mean=[" << em << "]";
+                warn[j] = o.str();
+            }
+        });
+        for (const auto& w : warn)
+            if (!w.empty()) std::clog << w << std::endl;
         if (nj)
         {
             const auto c0 = std::chrono::steady_clock::now();
-            check(nc_viterbi_packed(ctx_, nj, off.data(), mean.data(), stdv.data(), start.data(), nullptr, mid.data(),
-                                    pm.data(), st.data(), NC_MEM_HOST, path.data(), states.data(), moves.data()),
+            check(nc_viterbi_packed(ctx_, nj, off.data(), mean, stdv, start, nullptr, mid.data(),
+                                    pm.data(), st.data(), NC_MEM_HOST, path.data(), states, moves),
                   "nc_viterbi_packed");
             viterbi_call_s += std::chrono::duration< double >(std::chrono::steady_clock::now() - c0).count();
             viterbi_kernel_ms += nc_ctx_last_kernel_ms(ctx_);
             viterbi_events += off.back();
         }
-        // ---- rank candidates per read (:711-750, :808-836)
+        // ---- pass 3 (parallel over reads): rank the candidates of a read (:711-750, :808-836), assemble the sequences
         auto seq_of = [&](size_t j) {
             uint32_t n = (uint32_t)(off[j + 1] - off[j]);
-            uint32_t need = nc_base_seq(n, states.data() + off[j], moves.data() + off[j], nullptr, 0);
+            uint32_t need = nc_base_seq(n, states + off[j], moves + off[j], nullptr, 0);
             std::string s(need, 'N');
-            nc_base_seq(n, states.data() + off[j], moves.data() + off[j], &s[0], need);
+            nc_base_seq(n, states + off[j], moves + off[j], &s[0], need);
             return s;
         };
-        size_t j = 0;
-        while (j < jobs.size())
+        std::vector< std::pair< size_t, size_t > > spans;   // jobs [first, last) of each read that has any
+        for (size_t j = 0; j < jobs.size();)
         {
-            Read& rd = *reads[jobs[j].read];
             size_t je = j;
             while (je < jobs.size() && jobs[je].read == jobs[j].read) ++je;
+            spans.push_back(std::make_pair(j, je));
+            j = je;
+        }
+        std::vector< std::string > info(spans.size());
+        parallel_for(spans.size(), opt_.host_threads, [&](size_t k) {
+            const size_t j = spans[k].first, je = spans[k].second;
+            Read& rd = *reads[jobs[j].read];
+            std::ostringstream lg;
             if (rd.scale_strands_together)
             {
                 // jobs come in (strand 0, strand 1) pairs per candidate; best = last of a stable ascending sort by the sum
                 size_t best = j;
                 float best_sum = path[j] + path[j + 1];
-                for (size_t q = j + 2; q < je; q += 2)
+                for (size_t q = j + 2; q + 1 < je; q += 2)
                 {
                     float s = path[q] + path[q + 1];
                     if (!(s < best_sum)) { best = q; best_sum = s; }
@@ -569,8 +630,9 @@ void Pipeline::basecall_reads(std::vector< Read* >& reads)
                 const std::array< nc_st_params, 2 > best_st = rd.st_params_m.at(key);
                 for (unsigned s = 0; s < 2; ++s)
                 {
-                    NLOG(2, "best_model read [" << rd.read_id << "] strand [" << s << "] model [" << key[s] << "] pm_params ["
-                                << best_pm << "] st_params [" << best_st[s] << "] log_path_prob [" << path[best + s] << "]");
+                    if (opt_.log_level >= 2)
+                        lg << "best_model read [" << rd.read_id << "] strand [" << s << "] model [" << key[s] << "] pm_params ["
+                           << best_pm << "] st_params [" << best_st[s] << "] log_path_prob [" << path[best + s] << "]\n";
                     rd.preferred_model[s][s] = key[s];
                     rd.pm_params_m[rd.preferred_model[s]] = best_pm;
                     rd.st_params_m[rd.preferred_model[s]][s] = best_st[s];
@@ -588,17 +650,20 @@ void Pipeline::basecall_reads(std::vector< Read* >& reads)
                         if (jobs[q].strand == s && (best == SIZE_MAX || !(path[q] < path[best]))) best = q;
                     if (best == SIZE_MAX) continue;
                     const Model_Key key = jobs[best].key;
-                    NLOG(2, "best_model read [" << rd.read_id << "] strand [" << s << "] model [" << key[s] << "] pm_params ["
-                                << rd.pm_params_m.at(key) << "] st_params [" << rd.st_params_m.at(key)[s]
-                                << "] log_path_prob [" << path[best] << "]");
+                    if (opt_.log_level >= 2)
+                        lg << "best_model read [" << rd.read_id << "] strand [" << s << "] model [" << key[s] << "] pm_params ["
+                           << rd.pm_params_m.at(key) << "] st_params [" << rd.st_params_m.at(key)[s]
+                           << "] log_path_prob [" << path[best] << "]\n";
                     rd.preferred_model[s][s] = key[s];
                     rd.base_seq[s] = seq_of(best);
                     rd.log_path_prob[s] = path[best];
                     rd.called[s] = true;
                 }
             }
-            j = je;
-        }
+            info[k] = lg.str();
+        });
+        for (const auto& l : info)
+            if (!l.empty()) std::clog << l << std::flush;
         r0 = r1;
     }
 }

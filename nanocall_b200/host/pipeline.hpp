@@ -54,6 +54,7 @@ struct Options
     std::string model_fofn;        // file of "strand:file" lines (nanocall.cpp:118-127)
     std::string trans_fn;          // custom initial state transitions (nanocall.cpp:180-193)
     std::string data_dir;          // where builtin_models.{bin,txt} live
+    unsigned host_threads = 4;     // helper threads of a dispatcher for its per-read host work (packing, base sequences)
 };
 
 struct Strand_Events
@@ -119,6 +120,15 @@ public:
 private:
     void check(int rc, const char* what) const;
     nc_st_params default_st() const { nc_st_params s; s.p_stay = opt_.pr_stay; s.p_skip = opt_.pr_skip; return s; }
+    // grow-only page-locked staging buffers of the Viterbi calls (nc_host_alloc): events in, states / moves out
+    struct Pinned
+    {
+        void* p = nullptr;
+        size_t cap = 0;
+        void* reserve(size_t bytes);
+        ~Pinned();
+    };
+    Pinned pin_mean_, pin_stdv_, pin_start_, pin_states_, pin_moves_;
     Options opt_;
     nc_ctx* ctx_ = nullptr;
     std::map< std::string, Model > models_;  // ordered by name, as Pore_Model_Dict (std::map)
