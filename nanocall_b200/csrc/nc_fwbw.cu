@@ -73,7 +73,7 @@ __device__ __forceinline__ float fold_logsum_in_order(float acc, const int n, Ge
 // When every index is confirmed the a_k are by induction the sequential chain's values and the last live lane's
 // a + t is the result; otherwise the recomputed indices are the next guess (the first unconfirmed lane is certainly
 // right then).  After three rounds, or when a term exceeds the running value (start of a chain), the block is folded
-// term by term.  lst: 36 floats, 16-byte aligned, private to the warp.
+// term by term.  lst: 40 floats, 16-byte aligned, private to the warp.
 template < typename TB >
 __device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl, const int lane, float* __restrict__ lst)
 {
@@ -93,16 +93,19 @@ __device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl,
         {
             const float t = tbl.load(e);
             if (live) lst[r] = t;
-            if (lane < 4) lst[L + lane] = 0.0f;
+            if (lane < 8) lst[L + lane] = 0.0f;
             __syncwarp();
             float a = acc;
+            float4 v = *reinterpret_cast< const float4* >(lst);
             for (int k = 0; k < L; k += 4)
             {
-                const float4 v = *reinterpret_cast< const float4* >(lst + k);
+                // the next four increments are fetched before these are added: the chain of FADDs never waits for a load
+                const float4 vn = *reinterpret_cast< const float4* >(lst + k + 4);
                 a = (k + 0 < r) ? __fadd_rn(a, v.x) : a;
                 a = (k + 1 < r) ? __fadd_rn(a, v.y) : a;
                 a = (k + 2 < r) ? __fadd_rn(a, v.z) : a;
                 a = (k + 3 < r) ? __fadd_rn(a, v.w) : a;
+                v = vn;
             }
             __syncwarp();
             const unsigned e2 = tbl.addr(live ? __fsub_rn(a, x) : INF);

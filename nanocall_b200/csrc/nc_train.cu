@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 namespace {
 
@@ -61,6 +62,22 @@ int ensure_train_tables(nc_ctx* ctx)
     NC_CUDA(ctx, cudaFuncSetAttribute(nc::pm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nc::pm_stats_smem_bytes()));
     NC_CUDA(ctx, cudaFuncSetAttribute(nc::st_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nc::st_stats_smem_bytes()));
     return NC_OK;
+}
+
+// fn(i) for i in [0, n) on up to n_threads host threads (the per-group host work of a wave: job descriptors with their
+// transition LUTs before the launch, the 3x3 solves after it)
+template < typename Fn >
+void parallel_for(size_t n, unsigned n_threads, Fn fn)
+{
+    n_threads = (unsigned)std::min< size_t >(std::min(n_threads, 8u), (n + 255) / 256);
+    if (n_threads <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+    std::vector< std::thread > th;
+    for (unsigned t = 0; t < n_threads; ++t)
+        th.emplace_back([&, t] {
+            const size_t a = n * t / n_threads, b = n * (t + 1) / n_threads;
+            for (size_t i = a; i < b; ++i) fn(i);
+        });
+    for (auto& x : th) x.join();
 }
 
 void fill_job(nc::DevJob& J, int model, const nc_pm_params& pm, const nc_st_params& st)
@@ -402,9 +419,7 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
                 // Parameter_Trainer.hpp:443-444
                 G.log_p_stay[st] = std::log(in[g1].st[st].p_stay);
                 G.log_p_step_4[st] = (float)(std::log(1.0 - in[g1].st[st].p_stay - in[g1].st[st].p_skip) - std::log(4.0));
-                nc::DevJob J;
-                fill_job(J, in[g1].model_id[st], in[g1].pm, in[g1].st[st]);
-                w.jobs.push_back(J);
+                w.jobs.push_back(nc::DevJob());   // filled below, in parallel
             }
             for (uint32_t s = seq_off[g1]; s < seq_off[g1 + 1]; ++s)
             {
@@ -425,14 +440,18 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
             w.groups.push_back(G);
             ++g1;
         }
+        parallel_for(g1 - g0, ctx->host_threads, [&](size_t k) {
+            for (int st = 0; st < 2; ++st) fill_job(w.jobs[2 * k + st], in[g0 + k].model_id[st], in[g0 + k].pm, in[g0 + k].st[st]);
+        });
         if ((rc = run_wave(ctx, w, (const float*)ctx->fb_mean.p, (const float*)ctx->fb_stdv.p, (const float*)ctx->fb_start.p,
                            nullptr, opts->train_scaling != 0, opts->train_transitions != 0,
                            lz, pm_rows, st_acc)) != NC_OK)
             return rc;
         kernel_ms += ctx->last_kernel_ms;
         // ---- finish every group of the wave on the host (train_one_round, :541-579)
-        for (uint32_t g = g0; g < g1; ++g)
+        parallel_for(g1 - g0, ctx->host_threads, [&](size_t gk)
         {
+            const uint32_t g = g0 + (uint32_t)gk;
             const nc::FbGroup& G = w.groups[g - g0];
             nc_train_out& o = out[g];
             float fit = 0.0f;
@@ -452,14 +471,14 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
                 finish_pm(n_ev, pm_rows.data() + 6 * first.ev_out, mean + base + first.ev_off, yfix.data() + first.ev_off,
                           start + base + first.ev_off, opts->train_drift != 0, in[g].pm, o.pm, done);
                 o.done = done;
-                if (done) continue;  // new_st_params = crt_st_params (:566-570)
+                if (done) return;  // new_st_params = crt_st_params (:566-570)
             }
             if (opts->train_transitions)
             {
                 o.st[0] = finish_st(st_acc.data() + (size_t)(g - g0) * 6);
                 o.st[1] = finish_st(st_acc.data() + (size_t)(g - g0) * 6 + 3);
             }
-        }
+        });
         g0 = g1;
     }
     ctx->last_kernel_ms = kernel_ms;
