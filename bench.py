@@ -15,8 +15,11 @@ JSON line keys beyond the base contract:
                 kernel's own launch duration (CUDA events on the context's stream around each launch);
                 `traffic` = DRAM bytes per launch from the committed ncu capture (the kernel streams the alpha
                 columns, 16 KiB/event, by design: DESIGN.md K1a)
-  roofline_fp32 algorithmic FP32 work: 245,600 FP32 op/event against 148 SMs x 128 lanes x
-                SM clock measured under load (> 1: class sharing removes 2/3 of the edge operations)
+  roofline_issue executed work: the kernel's warp instructions per event (ncu smsp__inst_executed on this very launch,
+                profiles/r2_ncu_viterbi_alpha_10kx10k_summary.md) x events/s against the issue peak of 148 SMs x 4
+                sub-partitions x SM clock under load; the FMA-heavy pipe, the busiest one, was 68.8 % active in that capture.
+                (The algorithmic count of SURVEY 8d, 245,600 FP32 op/event, is NOT used as a roof: sharing the class maxima
+                removes two thirds of the per-edge operations, so a fraction built on it exceeds 1.)
   roofline_rf   what binds (profiles/r1_viterbi_alpha_experiments.md): register-file operand reads,
                 404 per thread and column, against the measured 2 reads per cycle and lane
   cpu_baseline  the reference's own Viterbi (oracle/_ref, kind "reference"; the C port otherwise)
@@ -50,7 +53,11 @@ HBM_BYTES_PER_EVENT = 4112
 FP32_OPS_PER_EVENT = 245600
 RF_READS_PER_EVENT = 404 * 512  # operand reads per thread and column x threads (nc_viterbi_alpha.cu header)
 # dram__bytes_read.sum + dram__bytes_write.sum per event of viterbi_alpha_kernel, from the committed capture
-NCU_DRAM_BYTES_PER_EVENT = {"viterbi_alpha_kernel": 17022.0, "source": "profiles/r1_ncu_viterbi_alpha_final_summary.md"}
+# measured on the bench's own launch (10000 reads x 10000 events, one kernel): 1.6387 TB written + 47.4 GB read
+NCU_DRAM_BYTES_PER_EVENT = {"viterbi_alpha_kernel": 16862.0, "source": "profiles/r2_ncu_viterbi_alpha_10kx10k_summary.md"}
+# executed work of the same launch: smsp__inst_executed.sum = 248.68e9 warp instructions for 1e8 events
+NCU_WARP_INSTR_PER_EVENT = {"viterbi_alpha_kernel": 2486.8, "fmaheavy_pipe_pct": 68.8, "issue_active_pct": 54.8,
+                            "source": "profiles/r2_ncu_viterbi_alpha_10kx10k_summary.md"}
 MODEL = "r73.t.006.ont.model"
 
 
@@ -476,11 +483,17 @@ def main():
                          "peak_kind": peak_kind, "kernel": kname, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": HBM_BYTES_PER_EVENT * total,
                          "algorithmic_bytes_per_event": HBM_BYTES_PER_EVENT},
-            "roofline_fp32": {"bound": "fp32_issue", "achieved": per_gpu_evs * FP32_OPS_PER_EVENT / 1e12,
-                              "peak": fp32_peak, "unit": "Tinstr/s", "frac": per_gpu_evs * FP32_OPS_PER_EVENT / 1e12 / fp32_peak,
-                              "algorithmic_ops_per_event": FP32_OPS_PER_EVENT,
-                              "peak_kind": f"{n_sms} SMs x 128 lanes x {sm_mhz:.0f} MHz under load"},
         }
+        if kname in NCU_WARP_INSTR_PER_EVENT:
+            wi = NCU_WARP_INSTR_PER_EVENT[kname]
+            issue_peak = n_sms * 4 * sm_mhz * 1e6 / 1e12   # T warp-instructions/s
+            line["roofline_issue"] = {"bound": "warp_issue", "achieved": per_gpu_evs * wi / 1e12, "peak": issue_peak,
+                                      "unit": "T warp-instr/s", "frac": per_gpu_evs * wi / 1e12 / issue_peak,
+                                      "warp_instructions_per_event": wi, "fmaheavy_pipe_pct_ncu": NCU_WARP_INSTR_PER_EVENT["fmaheavy_pipe_pct"],
+                                      "issue_active_pct_ncu": NCU_WARP_INSTR_PER_EVENT["issue_active_pct"],
+                                      "source": NCU_WARP_INSTR_PER_EVENT["source"],
+                                      "algorithmic_fp32_ops_per_event": FP32_OPS_PER_EVENT,
+                                      "peak_kind": f"{n_sms} SMs x 4 sub-partitions x {sm_mhz:.0f} MHz under load"}
         if args.vit_mode != "backpointer":
             rf_peak = n_sms * 128 * 2 * sm_mhz * 1e6 / 1e12
             line["roofline_rf"] = {"bound": "register_operand_reads", "achieved": per_gpu_evs * RF_READS_PER_EVENT / 1e12,

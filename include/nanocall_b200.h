@@ -162,6 +162,16 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
                          const float* mean, const float* stdv, const float* start,
                          const nc_train_in* in, const nc_train_opts* opts, nc_train_out* out);
 
+/* Custom initial state transitions: nanocall's --trans (nanocall.cpp:180-193; file format of
+ * State_Transitions::operator>>, State_Transitions.hpp:237-252): n_edges edges from[k] -> to[k] with log probability
+ * logp[k], in FILE ORDER.  From then on every Viterbi job and every training strand whose transition parameters EQUAL
+ * (p_stay_default, p_skip_default) -- State_Transition_Parameters::is_default(), State_Transitions.hpp:34-37 -- uses this
+ * table (kernels that walk stored predecessor / successor lists) instead of the parametric compute_transitions_fast table;
+ * all others keep the parametric table, exactly as basecall_strand (nanocall.cpp:651-661) and fill_train_data
+ * (Parameter_Trainer.hpp:118-131) choose.  n_edges == 0 removes the custom table. */
+int nc_ctx_set_default_transitions(nc_ctx* ctx, float p_stay_default, float p_skip_default, uint32_t n_edges,
+                                   const uint16_t* from, const uint16_t* to, const float* logp);
+
 /* Page-locked host memory for the event / state / move arrays of NC_MEM_HOST calls.  Optional: any host memory works,
  * but only pinned buffers are copied at full PCIe rate and let nc_viterbi_packed stream the events behind the kernel
  * launch.  nc_host_alloc returns NULL when the allocation fails (or there is no CUDA device). */

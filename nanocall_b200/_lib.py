@@ -66,6 +66,7 @@ SYMBOLS = {
     "nc_fwbw": (C.c_int, [_vp, _i32, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_f)]),
     "nc_train_round_batch": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nc_ctx_train_stats": (C.c_int, [_vp, _vp, C.c_int]),
+    "nc_ctx_set_default_transitions": (C.c_int, [_vp, _f, _f, _u32, _vp, _vp, _vp]),
     "nc_host_alloc": (_vp, [C.c_size_t]),
     "nc_host_free": (None, [_vp]),
     "nc_mean_stdv": (None, [_u32, _vp, C.POINTER(_f), C.POINTER(_f)]),

@@ -98,6 +98,14 @@ class Context:
         keys = ("emission_ms", "fwbw_ms", "pm_stats_ms", "st_stats_ms", "events", "launches", "waves")
         return {k: float(v) for k, v in zip(keys, out)}
 
+    def set_default_transitions(self, p_stay, p_skip, edges_from=None, edges_to=None, logp=None):
+        """Custom initial transition table (--trans): edges in file order; None removes it."""
+        if edges_from is None:
+            self._check(self.lib.nc_ctx_set_default_transitions(self.h, float(p_stay), float(p_skip), 0, None, None, None))
+            return
+        f, t, lp = _as(edges_from, np.uint16), _as(edges_to, np.uint16), _as(logp, np.float32)
+        self._check(self.lib.nc_ctx_set_default_transitions(self.h, float(p_stay), float(p_skip), f.size, _ptr(f), _ptr(t), _ptr(lp)))
+
     def set_viterbi_mode(self, mode):
         """L.NC_VIT_AUTO (alpha-column kernel where it fits) or L.NC_VIT_BACKPOINTER."""
         self._check(self.lib.nc_ctx_set_viterbi_mode(self.h, int(mode)))

@@ -6,7 +6,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <thread>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -88,7 +90,9 @@ void nc_ctx_destroy(nc_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : { &ctx->jobs, &ctx->order, &ctx->counter, &ctx->path, &ctx->mean, &ctx->stdv, &ctx->start,
                        &ctx->lstd, &ctx->states, &ctx->moves, &ctx->tb, &ctx->fb_scratch, &ctx->fb_seqs, &ctx->fb_groups, &ctx->fb_jobs,
-                       &ctx->fb_lz, &ctx->fb_pm, &ctx->fb_st, &ctx->fb_counter, &ctx->fb_mean, &ctx->fb_stdv, &ctx->fb_start, &ctx->fb_lstd })
+                       &ctx->fb_lz, &ctx->fb_pm, &ctx->fb_st, &ctx->fb_counter, &ctx->fb_mean, &ctx->fb_stdv, &ctx->fb_start, &ctx->fb_lstd,
+                       &ctx->gen_from_off, &ctx->gen_from_idx, &ctx->gen_from_lp, &ctx->gen_to_off, &ctx->gen_to_idx, &ctx->gen_to_lp,
+                       &ctx->gen_bp, &ctx->gen_order, &ctx->gen_counter })
         dev_free(*b);
     if (ctx->d_models) cudaFree(ctx->d_models);
     if (ctx->d_bp) cudaFree(ctx->d_bp);
@@ -193,6 +197,47 @@ int nc_model_stats(nc_ctx* ctx, int model_id, float* mean, float* stdv)
     return NC_OK;
 }
 
+int nc_ctx_set_default_transitions(nc_ctx* ctx, float p_stay_default, float p_skip_default, uint32_t n_edges,
+                                   const uint16_t* from, const uint16_t* to, const float* logp)
+{
+    if (!ctx) return NC_ERR_ARG;
+    NC_CUDA(ctx, cudaSetDevice(ctx->device));
+    NC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_edges == 0) { ctx->gen_on = false; return NC_OK; }
+    if (!from || !to || !logp) NC_FAIL(ctx, NC_ERR_ARG, "nc_ctx_set_default_transitions: NULL argument");
+    for (uint32_t k = 0; k < n_edges; ++k)
+        if (from[k] >= NC_N_STATES || to[k] >= NC_N_STATES) NC_FAIL(ctx, NC_ERR_ARG, "nc_ctx_set_default_transitions: edge %u: state out of range", k);
+    // to lists: the edges of a source in file order (to_v as State_Transitions::operator>> fills it, :237-252);
+    // from lists: built source by source, ascending (update_fields, :79-99)
+    std::vector< unsigned > to_off(NC_N_STATES + 1, 0), from_off(NC_N_STATES + 1, 0), to_idx(n_edges), from_idx(n_edges);
+    std::vector< float > to_lp(n_edges), from_lp(n_edges);
+    for (uint32_t k = 0; k < n_edges; ++k) { ++to_off[from[k] + 1]; ++from_off[to[k] + 1]; }
+    for (unsigned i = 0; i < NC_N_STATES; ++i) { to_off[i + 1] += to_off[i]; from_off[i + 1] += from_off[i]; }
+    {
+        std::vector< unsigned > fill(to_off.begin(), to_off.end() - 1);
+        for (uint32_t k = 0; k < n_edges; ++k) { const unsigned at = fill[from[k]]++; to_idx[at] = to[k]; to_lp[at] = logp[k]; }
+        std::vector< unsigned > ffill(from_off.begin(), from_off.end() - 1);
+        for (unsigned i = 0; i < NC_N_STATES; ++i)
+            for (unsigned e = to_off[i]; e < to_off[i + 1]; ++e) { const unsigned at = ffill[to_idx[e]]++; from_idx[at] = i; from_lp[at] = to_lp[e]; }
+    }
+    int rc;
+    struct Up { DevBuf* b; const void* src; size_t bytes; };
+    const Up ups[] = { { &ctx->gen_from_off, from_off.data(), from_off.size() * 4 }, { &ctx->gen_from_idx, from_idx.data(), from_idx.size() * 4 },
+                       { &ctx->gen_from_lp, from_lp.data(), from_lp.size() * 4 }, { &ctx->gen_to_off, to_off.data(), to_off.size() * 4 },
+                       { &ctx->gen_to_idx, to_idx.data(), to_idx.size() * 4 }, { &ctx->gen_to_lp, to_lp.data(), to_lp.size() * 4 } };
+    for (const Up& u : ups)
+    {
+        if ((rc = dev_reserve(ctx, *u.b, u.bytes)) != NC_OK) return rc;
+        NC_CUDA(ctx, cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice));
+    }
+    NC_CUDA(ctx, cudaFuncSetAttribute(nc::viterbi_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nc::viterbi_generic_smem_bytes()));
+    NC_CUDA(ctx, cudaFuncSetAttribute(nc::fwbw_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nc::fwbw_generic_smem_bytes()));
+    ctx->gen_default.p_stay = p_stay_default;
+    ctx->gen_default.p_skip = p_skip_default;
+    ctx->gen_on = true;
+    return NC_OK;
+}
+
 int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
                       const float* mean, const float* stdv, const float* start, const float* log_stdv,
                       const int32_t* model_id, const nc_pm_params* pm, const nc_st_params* st,
@@ -257,15 +302,26 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         while (fwd > 1 && fwd + tb_ctas_for(fwd) > ctas) --fwd;
         return fwd;
     };
-    std::vector< unsigned > order(n_jobs);
-    std::iota(order.begin(), order.end(), 0u);
+    // jobs whose transition parameters are the defaults while a custom table is in force (--trans) go to the
+    // list-walking kernel; the rest of this function deals with the others (n_jobs_p of them)
+    std::vector< unsigned > order, order_g;
+    order.reserve(n_jobs);
+    for (uint32_t k = 0; k < n_jobs; ++k)
+    {
+        const bool gen = ctx->gen_on && st[k].p_stay == ctx->gen_default.p_stay && st[k].p_skip == ctx->gen_default.p_skip;
+        (gen ? order_g : order).push_back(k);
+    }
+    const uint32_t n_jobs_all = n_jobs;
+    n_jobs = (uint32_t)order.size();
     std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return jobs[a].n_events > jobs[b].n_events; });
+    std::stable_sort(order_g.begin(), order_g.end(), [&](unsigned a, unsigned b) { return jobs[a].n_events > jobs[b].n_events; });
     // order = [long jobs (backpointer form) | the rest (alpha form)], each longest first
     uint32_t alpha_max_len = 0xffffffffu;
     if (want_path) alpha_max_len = (uint32_t)std::min< size_t >(ctx->bp_bytes / a_col, 0x7fffffffu);
     if (ctx->vit_mode == NC_VIT_BACKPOINTER) alpha_max_len = 0;   // forced backpointer form (tests, A/B measurements)
     uint32_t n_long = 0;
     while (n_long < n_jobs && jobs[order[n_long]].n_events > alpha_max_len) ++n_long;
+    if (n_jobs) max_len = jobs[order[0]].n_events;   // (of the jobs this part handles)
     unsigned grid_b = 0, fwd_a = 0, tb_a = 0;
     size_t slab_b = 0, slab_a = 0, pool_b = 0;
     for (;;)
@@ -326,15 +382,27 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     }
 
     int rc;
-    if ((rc = dev_reserve(ctx, ctx->jobs, n_jobs * sizeof(nc::DevJob))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->order, n_jobs * sizeof(unsigned))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->jobs, n_jobs_all * sizeof(nc::DevJob))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->order, std::max< size_t >(1, n_jobs) * sizeof(unsigned))) != NC_OK) return rc;
+    // the list-walking kernel's share: its job order, a work counter, and one slab of 16-bit backpointers per CTA
+    unsigned grid_g = 0;
+    size_t slab_g = 0;
+    if (!order_g.empty())
+    {
+        slab_g = (size_t)jobs[order_g[0]].n_events * NC_N_STATES * sizeof(unsigned short);
+        grid_g = (unsigned)std::min< size_t >(order_g.size(), 2 * n_sms);
+        while (grid_g > 1 && (size_t)grid_g * slab_g > ((size_t)16 << 30)) --grid_g;
+        if ((rc = dev_reserve(ctx, ctx->gen_order, order_g.size() * sizeof(unsigned))) != NC_OK) return rc;
+        if ((rc = dev_reserve(ctx, ctx->gen_counter, sizeof(unsigned))) != NC_OK) return rc;
+        if (want_path && (rc = dev_reserve(ctx, ctx->gen_bp, (size_t)grid_g * slab_g)) != NC_OK) return rc;
+    }
     if ((rc = dev_reserve(ctx, ctx->counter, 2 * sizeof(unsigned))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->path, n_jobs * sizeof(float))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->path, n_jobs_all * sizeof(float))) != NC_OK) return rc;
     // alpha kernel control block: tickets | tail, head | release counter of every forward CTA | column allocator.
     // Every allocation of the call happens before its first asynchronous operation (a cudaFree inside dev_reserve is a
     // device-wide synchronisation, and an allocation failure must not leave copies or kernels in flight).
     const size_t tk_bytes = (size_t)n_short * sizeof(nc::TbTicket);
-    const size_t ctl_bytes = ((2 + 2 * (size_t)fwd_a) * sizeof(unsigned) + 15) & ~(size_t)15;
+    const size_t ctl_bytes = ((2 + 2 * (size_t)fwd_a + 80) * sizeof(unsigned) + 15) & ~(size_t)15;   // + phase words (diagnostics)
     const size_t ca_bytes = nc::viterbi_alpha_colalloc_bytes();
     if (n_short && want_path && (rc = dev_reserve(ctx, ctx->tb, tk_bytes + ctl_bytes + ca_bytes)) != NC_OK) return rc;
     const uint64_t base = ev_off[0];
@@ -350,7 +418,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         // Big batches in PINNED memory: the kernels start at once and the event arrays follow on a third stream in
         // chunks.  From pageable memory cudaMemcpyAsync is staged and blocks the host, so nothing would overlap
         // (and the chunking would only add small copies): such calls take the plain copy path.
-        stream_in = total >= ctx->stream_in_min_events;
+        stream_in = total >= ctx->stream_in_min_events && order_g.empty();   // (the list-walking kernel does not poll the landed counter)
         if (stream_in)
         {
             cudaPointerAttributes at;
@@ -372,8 +440,8 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         }                                                                                                             \
     } while (0)
     cudaStream_t s = ctx->stream;
-    NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), n_jobs * sizeof(nc::DevJob), cudaMemcpyHostToDevice, s));
-    NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->order.p, order.data(), n_jobs * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+    NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), n_jobs_all * sizeof(nc::DevJob), cudaMemcpyHostToDevice, s));
+    if (n_jobs) NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->order.p, order.data(), n_jobs * sizeof(unsigned), cudaMemcpyHostToDevice, s));
     NC_CUDA_INFLIGHT(cudaMemsetAsync(ctx->counter.p, 0, 2 * sizeof(unsigned), s));
 
     nc::VitArgs a;
@@ -468,6 +536,23 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     }
     NC_CUDA_INFLIGHT(cudaEventRecord(ctx->ev0, s));
     ctx->last_launches = 0;
+    if (!order_g.empty())
+    {
+        nc::VitArgs gkn = a;
+        gkn.order = (const unsigned*)ctx->gen_order.p;
+        gkn.n_jobs = (unsigned)order_g.size();
+        gkn.next_job = (unsigned*)ctx->gen_counter.p;
+        gkn.bp_pool = (unsigned char*)ctx->gen_bp.p;
+        gkn.slab_bytes = slab_g;
+        gkn.landed = nullptr;
+        nc::GenTrans gt = { (const unsigned*)ctx->gen_from_off.p, (const unsigned*)ctx->gen_from_idx.p, (const float*)ctx->gen_from_lp.p,
+                            (const unsigned*)ctx->gen_to_off.p, (const unsigned*)ctx->gen_to_idx.p, (const float*)ctx->gen_to_lp.p };
+        NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->gen_order.p, order_g.data(), order_g.size() * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+        NC_CUDA_INFLIGHT(cudaMemsetAsync(ctx->gen_counter.p, 0, sizeof(unsigned), s));
+        nc::viterbi_generic_kernel<<< grid_g, 512, nc::viterbi_generic_smem_bytes(), s >>>(gkn, gt);
+        NC_CUDA_INFLIGHT(cudaGetLastError());
+        ++ctx->last_launches;
+    }
     if (n_long)
     {
         // on the second stream, so it runs next to the alpha kernel (grid_b + fwd_a + tb_a <= number of SMs)
@@ -515,8 +600,100 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     }
     NC_CUDA_INFLIGHT(cudaEventRecord(ctx->ev1, s));
 
+    // what the alpha grid looks like (diagnostics of a stalled or aborted grid): counters, forward CTAs and service warps by
+    // what they are doing (note_phase), tickets, the column allocator's free list.  Copies go through the copy stream so
+    // the snapshot can be taken while the kernel is still running.
+    auto alpha_state = [&]() -> std::string {
+        if (!(n_short && want_path)) return std::string();
+        cudaStream_t sc = ctx->stream3;
+        const size_t n_ctl = 2 + 2 * (size_t)fwd_a + 80;
+        std::vector< unsigned char > img(ca_bytes);
+        std::vector< unsigned > ctl(n_ctl, 0u);
+        std::vector< nc::TbTicket > tks(n_short);
+        unsigned started[2] = { 0, 0 };
+        cudaMemcpyAsync(img.data(), (char*)ctx->tb.p + tk_bytes + ctl_bytes, ca_bytes, cudaMemcpyDeviceToHost, sc);
+        cudaMemcpyAsync(ctl.data(), (char*)ctx->tb.p + tk_bytes, n_ctl * sizeof(unsigned), cudaMemcpyDeviceToHost, sc);
+        cudaMemcpyAsync(tks.data(), ctx->tb.p, tk_bytes, cudaMemcpyDeviceToHost, sc);
+        cudaMemcpyAsync(started, ctx->counter.p, sizeof started, cudaMemcpyDeviceToHost, sc);
+        cudaStreamSynchronize(sc);
+        cudaGetLastError();
+        const unsigned* w = reinterpret_cast< const unsigned* >(img.data());   // next_ticket, now_serving, n_free, max_free, start[], len[]
+        const unsigned nf = std::min(w[2], 1024u);
+        unsigned long long free_cols = 0;
+        unsigned largest = 0;
+        for (unsigned k = 0; k < nf; ++k) { free_cols += w[4 + 1024 + k]; largest = std::max(largest, w[4 + 1024 + k]); }
+        const unsigned* rel = ctl.data() + 2;
+        const unsigned* fph = rel + fwd_a;
+        const unsigned* sph = fph + fwd_a;
+        unsigned by_phase[16] = { 0 }, max_behind = 0, sum_done = 0, sum_rel = 0;
+        for (unsigned k = 0; k < fwd_a; ++k)
+        {
+            const unsigned ph = fph[k] & 15u, done = fph[k] >> 4;
+            ++by_phase[ph];
+            sum_done += done;
+            sum_rel += rel[k];
+            if (done > rel[k]) max_behind = std::max(max_behind, done - rel[k]);
+        }
+        unsigned ready_below = 0, ready_above = 0, first_unready = n_short;
+        for (unsigned k = 0; k < n_short; ++k)
+        {
+            if (tks[k].ready) ++(k < ctl[0] ? ready_below : ready_above);
+            else if (k < first_unready) first_unready = k;
+        }
+        unsigned sv_phase[8] = { 0 }, sv_min = 0xffffffffu, sv_max = 0;
+        for (unsigned k = 0; k < 16 * tb_a; ++k) { const unsigned v = sph[k]; ++sv_phase[v & 7u]; sv_min = std::min(sv_min, v >> 4); sv_max = std::max(sv_max, v >> 4); }
+        char d[1800];
+        std::snprintf(d, sizeof d, "alpha jobs %u (longest %u events), %u forward + %u service CTAs, handed out %u, tickets published %u, "
+                      "claimed by the traceback service %u, released %u; forward CTAs: %u not started, %u waiting for a release, %u waiting for columns, "
+                      "%u in the forward pass, %u publishing, %u waiting for input, %u done, %u gave up waiting for a release, %u gave up waiting for columns; "
+                      "their finished jobs %u, most unreleased jobs of one CTA %u; pool %zu columns, free %llu in %u extents (largest %u, bound %u), lock waiters %u; "
+                      "tickets ready below the published count %u, above it %u, first not ready %u; service warps: %u idle, %u waiting for a ticket, "
+                      "%u tracing, %u releasing columns, %u released, %u out of tickets, %u gave up (tickets %u..%u), %u releases after the abort",
+                      n_short, jobs[order[n_long]].n_events, fwd_a, tb_a, started[1], ctl[0], ctl[1], sum_rel,
+                      by_phase[0], by_phase[1], by_phase[2], by_phase[3], by_phase[4], by_phase[5], by_phase[6], by_phase[7], by_phase[8],
+                      sum_done, max_behind, slab_a / a_col, free_cols, nf, largest, w[3], w[0] - w[1], ready_below, ready_above, first_unready,
+                      sv_phase[0], sv_phase[1], sv_phase[2], sv_phase[3], sv_phase[4], sv_phase[5], sv_phase[6], sv_min, sv_max, ctl[2 + 2 * (size_t)fwd_a + 64]);
+        std::string out(d);
+        if (std::getenv("NC_DEBUG_STALL_S"))
+        {
+            // raw state: per forward CTA (finished jobs, releases, phase), per service warp (ticket, phase), unready tickets
+            // below the published count, the free list
+            char e[96];
+            out += "\n  forward CTAs (done/released/phase):";
+            for (unsigned k = 0; k < fwd_a; ++k) { std::snprintf(e, sizeof e, " %u/%u/%u", fph[k] >> 4, rel[k], fph[k] & 15u); out += e; }
+            out += "\n  service warps (ticket/phase):";
+            for (unsigned k = 0; k < 16 * tb_a; ++k) { std::snprintf(e, sizeof e, " %u/%u", sph[k] >> 4, sph[k] & 7u); out += e; }
+            out += "\n  tickets below the published count that are not ready:";
+            for (unsigned k = 0; k < std::min(ctl[0], n_short); ++k)
+                if (!tks[k].ready) { std::snprintf(e, sizeof e, " %u(job %u cta %u col0 %u)", k, tks[k].job, tks[k].slab, tks[k].col0); out += e; }
+            out += "\n  free extents (start+len):";
+            for (unsigned k = 0; k < std::min(nf, 64u); ++k) { std::snprintf(e, sizeof e, " %u+%u", w[4 + k], w[4 + 1024 + k]); out += e; }
+        }
+        return out;
+    };
+    // NC_DEBUG_STALL_S=<seconds>: if the kernels are still running after that long, print the grid's state and go on waiting
+    // (before the copies back: a copy into pageable memory blocks the host until the kernels are done)
+    if (const char* v = std::getenv("NC_DEBUG_STALL_S"))
+    {
+        const double lim = std::atof(v);
+        const auto t0 = std::chrono::steady_clock::now();
+        bool dumped = false;
+        while (cudaStreamQuery(s) == cudaErrorNotReady)
+        {
+            const double el = std::chrono::duration< double >(std::chrono::steady_clock::now() - t0).count();
+            if (!dumped && el > lim)
+            {
+                std::fprintf(stderr, "nc_viterbi_packed: still running after %.1f s: %s\n", el, alpha_state().c_str());
+                std::this_thread::sleep_for(std::chrono::milliseconds(500));
+                std::fprintf(stderr, "nc_viterbi_packed: 0.5 s later: %s\n", alpha_state().c_str());
+                dumped = true;
+            }
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        }
+        cudaGetLastError();
+    }
     NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->h_abort, ctx->d_abort, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-    NC_CUDA_INFLIGHT(cudaMemcpyAsync(path_logprob, ctx->path.p, n_jobs * sizeof(float), cudaMemcpyDeviceToHost, s));
+    NC_CUDA_INFLIGHT(cudaMemcpyAsync(path_logprob, ctx->path.p, n_jobs_all * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (mem == NC_MEM_HOST)
     {
         if (states) NC_CUDA_INFLIGHT(cudaMemcpyAsync(states + base, ctx->states.p, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
@@ -530,27 +707,10 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         static const char* const why[] = { "", "a forward CTA waited for its release slot", "a forward CTA waited for alpha columns",
                                            "a traceback warp waited for a ticket", "the column allocator's extent list overflowed" };
         const unsigned code = *ctx->h_abort;
-        // what the grid looked like when it gave up: jobs started / finished / claimed by the traceback service, and the
-        // column allocator's free list
-        char diag[256] = "";
-        if (n_short && want_path)
-        {
-            std::vector< unsigned char > img(ca_bytes);
-            unsigned ctl[2] = { 0, 0 }, started[2] = { 0, 0 };
-            cudaMemcpy(img.data(), (char*)ctx->tb.p + tk_bytes + ctl_bytes, ca_bytes, cudaMemcpyDeviceToHost);
-            cudaMemcpy(ctl, (char*)ctx->tb.p + tk_bytes, sizeof ctl, cudaMemcpyDeviceToHost);
-            cudaMemcpy(started, ctx->counter.p, sizeof started, cudaMemcpyDeviceToHost);
-            const unsigned* w = reinterpret_cast< const unsigned* >(img.data());   // lock, n_free, pad[2], start[], len[]
-            const unsigned nf = std::min(w[1], 1024u);
-            unsigned long long free_cols = 0;
-            unsigned largest = 0;
-            for (unsigned k = 0; k < nf; ++k) { free_cols += w[4 + 1024 + k]; largest = std::max(largest, w[4 + 1024 + k]); }
-            std::snprintf(diag, sizeof diag, "; alpha jobs %u (longest %u events), started %u, finished %u, claimed by the traceback service %u; "
-                          "pool %zu columns, free %llu in %u extents (largest %u), lock %u", n_short, jobs[order[n_long]].n_events,
-                          started[1], ctl[0], ctl[1], slab_a / a_col, free_cols, nf, largest, w[0]);
-        }
+        const std::string diag = alpha_state();
+        if (std::getenv("NC_DEBUG_STALL_S")) std::fprintf(stderr, "nc_viterbi_packed: after the abort: %s\n", diag.c_str());
         NC_FAIL(ctx, NC_ERR_STATE, "nc_viterbi_packed: the alpha-column kernel stopped without finishing (%s for more than %.0f s): "
-                "results of this call are invalid%s", code < 5 ? why[code] : "unknown reason", ctx->wait_limit_s, diag);
+                "results of this call are invalid%s%s", code < 5 ? why[code] : "unknown reason", ctx->wait_limit_s, diag.empty() ? "" : "; ", diag.c_str());
     }
     return NC_OK;
 #undef NC_CUDA_INFLIGHT

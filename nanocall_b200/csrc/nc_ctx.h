@@ -42,6 +42,11 @@ struct nc_ctx
     // grow-only scratch
     DevBuf jobs, order, counter, path, mean, stdv, start, lstd, states, moves, tb;
     DevBuf fb_scratch, fb_seqs, fb_groups, fb_jobs, fb_lz, fb_pm, fb_st, fb_counter, fb_mean, fb_stdv, fb_start, fb_lstd;
+    // custom default transition table (nc_ctx_set_default_transitions): in force for jobs / strands whose transition
+    // parameters equal gen_default
+    bool gen_on = false;
+    nc_st_params gen_default{ 0.f, 0.f };
+    DevBuf gen_from_off, gen_from_idx, gen_from_lp, gen_to_off, gen_to_idx, gen_to_lp, gen_bp, gen_order, gen_counter;
     unsigned* d_train_kmers = nullptr;
     unsigned n_train_kmers = 0;
     size_t fb_scratch_limit = 0;  // bytes of E|alpha|beta slabs per wave (0 = pick from free memory)
@@ -61,7 +66,7 @@ struct nc_ctx
 
 #define NC_FAIL(ctx, code, ...)                                        \
     do {                                                               \
-        char _b[512];                                                  \
+        char _b[2048];                                                 \
         std::snprintf(_b, sizeof _b, __VA_ARGS__);                     \
         (ctx)->err = _b;                                               \
         return (code);                                                 \

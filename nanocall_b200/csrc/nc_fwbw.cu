@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
         const unsigned seq = sm.item;
         if (seq >= a.n_seqs) break;
         const FbSeq& Q = a.seqs[seq];
+        if (Q.generic) continue;   // a custom transition table applies: fwbw_generic_kernel's sequence
         const DevJob& J = a.jobs[Q.job];
         const unsigned n = Q.n_events;
         const float* E = a.scratch + Q.slab;

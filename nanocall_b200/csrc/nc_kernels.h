@@ -80,7 +80,8 @@ struct FbSeq
     unsigned n_events;
     unsigned job;               // index into jobs: model + scaling + transition LUT of the sequence's strand
     unsigned strand;
-    unsigned pad;
+    unsigned generic;           // 1: the strand's transition parameters are the defaults and a custom table is in force
+                                // (fwbw_generic_kernel takes the sequence, fwbw_kernel skips it)
 };
 
 struct FbGroup
@@ -113,6 +114,22 @@ struct FbArgs
     float log_2pi;
     float log_n_states;
 };
+
+// An arbitrary transition table (nanocall --trans) as stored lists: predecessors of j in from_idx/from_lp
+// [from_off[j], from_off[j+1]) in ascending source order (ties in file order), successors in to_* in file order
+struct GenTrans
+{
+    const unsigned* from_off;   // 4097
+    const unsigned* from_idx;
+    const float* from_lp;
+    const unsigned* to_off;     // 4097
+    const unsigned* to_idx;
+    const float* to_lp;
+};
+__global__ void viterbi_generic_kernel(const VitArgs a, const GenTrans g);
+size_t viterbi_generic_smem_bytes();
+__global__ void fwbw_generic_kernel(const FbArgs a, const GenTrans g);   // uses next_item[1] as its work counter
+size_t fwbw_generic_smem_bytes();
 
 __global__ void emission_kernel(const FbArgs a);
 __global__ void fwbw_kernel(const FbArgs a);

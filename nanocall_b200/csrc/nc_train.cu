@@ -231,12 +231,12 @@ int run_wave(nc_ctx* ctx, const Wave& w, const float* d_mean, const float* d_std
     if ((rc = dev_reserve(ctx, ctx->fb_lz, ns * sizeof(float))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->fb_pm, std::max< size_t >(1, w.n_events) * 6 * sizeof(float))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->fb_st, std::max(1u, ng) * 6 * sizeof(float))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->fb_counter, sizeof(unsigned))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, ctx->fb_counter, 2 * sizeof(unsigned))) != NC_OK) return rc;
     cudaStream_t s = ctx->stream;
     NC_CUDA(ctx, cudaMemcpyAsync(ctx->fb_seqs.p, w.seqs.data(), ns * sizeof(nc::FbSeq), cudaMemcpyHostToDevice, s));
     if (ng) NC_CUDA(ctx, cudaMemcpyAsync(ctx->fb_groups.p, w.groups.data(), ng * sizeof(nc::FbGroup), cudaMemcpyHostToDevice, s));
     NC_CUDA(ctx, cudaMemcpyAsync(ctx->fb_jobs.p, w.jobs.data(), w.jobs.size() * sizeof(nc::DevJob), cudaMemcpyHostToDevice, s));
-    NC_CUDA(ctx, cudaMemsetAsync(ctx->fb_counter.p, 0, sizeof(unsigned), s));
+    NC_CUDA(ctx, cudaMemsetAsync(ctx->fb_counter.p, 0, 2 * sizeof(unsigned), s));
 
     nc::FbArgs a;
     a.jobs = (const nc::DevJob*)ctx->fb_jobs.p;
@@ -268,8 +268,19 @@ int run_wave(nc_ctx* ctx, const Wave& w, const float* d_mean, const float* d_std
     const unsigned grid = std::min< unsigned >(ns, 2u * (unsigned)ctx->prop.multiProcessorCount);
     nc::fwbw_kernel<<< grid, 512, nc::fwbw_smem_bytes(), s >>>(a);
     NC_CUDA(ctx, cudaGetLastError());
-    NC_CUDA(ctx, cudaEventRecord(ctx->evk[2], s));
     int launches = 2;
+    bool any_generic = false;
+    for (const auto& q : w.seqs) any_generic = any_generic || q.generic;
+    if (any_generic)
+    {
+        // sequences under the custom default transition table (nc_ctx_set_default_transitions): stored-list kernel
+        nc::GenTrans gt = { (const unsigned*)ctx->gen_from_off.p, (const unsigned*)ctx->gen_from_idx.p, (const float*)ctx->gen_from_lp.p,
+                            (const unsigned*)ctx->gen_to_off.p, (const unsigned*)ctx->gen_to_idx.p, (const float*)ctx->gen_to_lp.p };
+        nc::fwbw_generic_kernel<<< grid, 512, nc::fwbw_generic_smem_bytes(), s >>>(a, gt);
+        NC_CUDA(ctx, cudaGetLastError());
+        ++launches;
+    }
+    NC_CUDA(ctx, cudaEventRecord(ctx->evk[2], s));
     if (pm_stats)
     {
         nc::pm_stats_kernel<<< dim3(tiles, ns), 512, nc::pm_stats_smem_bytes(), s >>>(a);
@@ -349,6 +360,7 @@ int nc_fwbw(nc_ctx* ctx, int32_t model_id, const nc_pm_params* pm, const nc_st_p
     nc::FbSeq q;
     std::memset(&q, 0, sizeof q);
     q.n_events = n_events;
+    q.generic = ctx->gen_on && st->p_stay == ctx->gen_default.p_stay && st->p_skip == ctx->gen_default.p_skip;
     w.seqs.push_back(q);
     w.scratch_floats = (size_t)3 * n_events * NC_N_STATES;
     w.n_events = n_events;
@@ -431,6 +443,9 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
                 q.ev_out = w.n_events;
                 q.job = 2 * (g1 - g0) + seq_strand[s];
                 q.strand = seq_strand[s];
+                // State_Transition_Parameters::is_default() (Parameter_Trainer.hpp:118-131): the custom table, if any
+                q.generic = ctx->gen_on && in[g1].st[seq_strand[s]].p_stay == ctx->gen_default.p_stay
+                    && in[g1].st[seq_strand[s]].p_skip == ctx->gen_default.p_skip;
                 w.scratch_floats += (size_t)3 * q.n_events * NC_N_STATES;
                 w.n_events += q.n_events;
                 w.max_len = std::max(w.max_len, q.n_events);

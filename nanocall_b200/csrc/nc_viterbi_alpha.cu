@@ -305,7 +305,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
 // launches it cooperatively, which the driver refuses when that is impossible) and making progress.  Every such wait
 // is bounded: after a.wait_limit nanoseconds of back-off without progress (two minutes by default; a healthy wait is microseconds) the waiter
 // raises the abort word, every other wait loop sees it and the CTAs drain, and the host reports NC_ERR_STATE.
-__device__ __forceinline__ bool aborted(const VitArgs& a) { return ldv_abort(a.abort_word) != 0u; }
 // slept = nanoseconds this wait has asked __nanosleep for so far (the waiters back off to a few microseconds per poll, so
 // the sum tracks the elapsed time from below; SM cycle counters turned out not to be a reliable clock for this)
 __device__ __forceinline__ bool give_up(const VitArgs& a, unsigned long long slept, unsigned code)
@@ -326,9 +325,10 @@ constexpr int CA_MAX = 1024;
 constexpr unsigned CA_MAX_LIVE = 4;
 struct ColAlloc
 {
-    int lock;
+    unsigned next_ticket;     // ticket lock: FIFO, so no warp can be starved of the list by the others (a compare-and-swap spin
+    unsigned now_serving;     // lock let the forward warps nearest to its L2 slice shut the service warps out for minutes)
     unsigned n_free;
-    unsigned pad[2];
+    unsigned max_free;        // upper bound of the largest free extent: a waiter that cannot fit does not touch the lock
     unsigned start[CA_MAX];   // ascending
     unsigned len[CA_MAX];
 };
@@ -338,8 +338,13 @@ __device__ __forceinline__ void ca_lock(ColAlloc* A, int lane)
 {
     if (lane == 0)
     {
-        unsigned ns = 32;
-        while (atomicCAS(&A->lock, 0, 1) != 0) { __nanosleep(ns); if (ns < 2048) ns *= 2; }
+        const unsigned my = atomicAdd(&A->next_ticket, 1u);
+        for (;;)
+        {
+            const unsigned ahead = my - ld_acquire_u32(&A->now_serving);
+            if (ahead == 0u) break;
+            __nanosleep(ahead > 16u ? 2048u : ahead * 128u);   // a turn lasts about a microsecond
+        }
         __threadfence();
     }
     __syncwarp();
@@ -350,7 +355,7 @@ __device__ __forceinline__ void ca_unlock(ColAlloc* A, int lane)
     if (lane == 0)
     {
         __threadfence();
-        atomicExch(&A->lock, 0);
+        st_release_u32(&A->now_serving, ldv(&A->now_serving) + 1u);   // (only the holder writes it)
     }
 }
 // remove entry `at` of a list of nf entries (called with the lock held, by the whole warp)
@@ -373,12 +378,20 @@ __device__ __forceinline__ bool ca_alloc(ColAlloc* A, unsigned n, unsigned& s, i
     ca_lock(A, lane);
     const unsigned nf = ldv(&A->n_free);
     int found = -1;
+    unsigned longest = 0;
     for (unsigned base = 0; base < nf; base += 32)
     {
         const unsigned i = base + lane;
         const unsigned l = (i < nf) ? ldv(A->len + i) : 0u;
+        longest = l > longest ? l : longest;
         const unsigned m = __ballot_sync(0xffffffffu, l >= n);
         if (m) { found = (int)base + __ffs(m) - 1; break; }
+    }
+    if (found < 0)
+    {
+        // the whole list was read: the bound becomes exact (only a release can raise it again)
+        longest = __reduce_max_sync(0xffffffffu, longest);
+        if (lane == 0) stv(&A->max_free, longest);
     }
     if (found >= 0)
     {
@@ -409,20 +422,25 @@ __device__ __forceinline__ void ca_free(ColAlloc* A, unsigned s, unsigned n, int
     const bool join_prev = idx > 0 && ldv(A->start + idx - 1) + ldv(A->len + idx - 1) == s;
     const bool join_next = idx < nf && s + n == ldv(A->start + idx);
     __syncwarp();
+    unsigned merged = n;   // length of the free extent that now holds the released columns
     if (join_prev && join_next)
     {
-        const unsigned add = n + ldv(A->len + idx);
+        merged = n + ldv(A->len + idx) + ldv(A->len + idx - 1);
         __syncwarp();
-        if (lane == 0) stv(A->len + idx - 1, ldv(A->len + idx - 1) + add);
+        if (lane == 0) stv(A->len + idx - 1, merged);
         ca_remove(A, idx, nf, lane);
     }
     else if (join_prev)
     {
-        if (lane == 0) stv(A->len + idx - 1, ldv(A->len + idx - 1) + n);
+        merged = ldv(A->len + idx - 1) + n;
+        __syncwarp();
+        if (lane == 0) stv(A->len + idx - 1, merged);
     }
     else if (join_next)
     {
-        if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, ldv(A->len + idx) + n); }
+        merged = ldv(A->len + idx) + n;
+        __syncwarp();
+        if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, merged); }
     }
     else if (nf < (unsigned)CA_MAX)
     {
@@ -442,7 +460,14 @@ __device__ __forceinline__ void ca_free(ColAlloc* A, unsigned s, unsigned n, int
     }
     else if (lane == 0) atomicCAS(abort_word, 0u, 4u);   // extent list full: an error, not a silent leak (the host also
                                                          // refuses launches whose live jobs could exceed the list)
+    if (lane == 0 && merged > ldv(&A->max_free)) stv(&A->max_free, merged);
     ca_unlock(A, lane);
+}
+
+// phase word of a forward CTA (diagnostics of an aborted grid): (jobs finished << 4) | what it is doing
+__device__ __forceinline__ void note_phase(const VitArgs& a, unsigned fwd_id, unsigned jobs_done, unsigned phase)
+{
+    if (a.slab_free) *reinterpret_cast< volatile unsigned* >(a.slab_free + a.n_fwd + fwd_id) = (jobs_done << 4) | phase;
 }
 
 __device__ __forceinline__ void forward_cta(const VitArgs& a)
@@ -470,13 +495,14 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
         if (t == 0) sm.job = atomicAdd(a.next_job, 1u);
         __syncthreads();
         const unsigned q = sm.job;
-        if (q >= a.n_jobs) break;
+        if (q >= a.n_jobs) { if (t == 0) note_phase(a, fwd_id, jobs_done, 6u); break; }
         const unsigned job_idx = a.order[q];
         const DevJob& J = a.jobs[job_idx];
         const unsigned n = J.n_events;
         const unsigned long long off = J.ev_off;
         if (a.landed)
         {
+            if (t == 0) note_phase(a, fwd_id, jobs_done, 5u);
             if (t == 0) wait_events_landed(a, off, n);
             __syncthreads();
         }
@@ -491,6 +517,7 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
                 unsigned ns = 64;
                 unsigned long long slept = 0;
                 bool gave_up = false;
+                if (lane == 0) note_phase(a, fwd_id, jobs_done, 1u);
                 if (lane == 0)
                     while (ld_acquire_u32(a.slab_free + fwd_id) + CA_MAX_LIVE <= jobs_done)
                     {
@@ -500,11 +527,17 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
                         if (ns < 4096) ns *= 2;
                     }
                 gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
+                const unsigned gave_up_at = gave_up ? 7u : 8u;   // 7: waiting for a release, 8: waiting for columns
                 unsigned got = 0;
                 ns = 128;
                 slept = 0;
-                while (!gave_up && !ca_alloc(CA, n, got, lane))
+                if (lane == 0) note_phase(a, fwd_id, jobs_done, 2u);
+                while (!gave_up)
                 {
+                    // the list is only locked when the job can fit: waiters that cannot fit poll one word, so they do not
+                    // keep the lock from the service warps whose releases they are waiting for
+                    const bool may_fit = __shfl_sync(0xffffffffu, ldv(&CA->max_free) >= n, 0);
+                    if (may_fit && ca_alloc(CA, n, got, lane)) break;
                     if (give_up(a, slept, 2u)) gave_up = true;
                     gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
                     __nanosleep(ns);
@@ -513,6 +546,7 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
                 }
                 if (lane == 0)
                 {
+                    note_phase(a, fwd_id, jobs_done, gave_up ? gave_up_at : 3u);
                     sm.col0 = gave_up ? 0xffffffffu : got;
                     if (a.stats) atomicAdd(a.stats + 1, (unsigned long long)(clock64() - c0));
                 }
@@ -736,6 +770,7 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
             __syncthreads();
             if (t == 0)
             {
+                note_phase(a, fwd_id, jobs_done, 4u);
                 const unsigned slot = atomicAdd(a.tb_tail, 1u);
                 TbTicket& tk = a.tickets[slot];
                 tk.job = job_idx;
@@ -757,15 +792,25 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
 // guesses are verified against the state the successor block actually reached and wrong blocks are re-walked until
 // nothing changes -- exactly the sequential traceback, in ~(n/32 + depth) dependent steps.  Every step evaluates
 // the arg max from the stored alpha column (tb_step).
+#ifdef NC_NO_SERVICE_PHASE
+#define NC_SVC_ON false
+#define NC_SVC_PHASE(code) do { } while (0)
+#else
+#define NC_SVC_ON true
+#define NC_SVC_PHASE(code) do { if (lane == 0) *phase = (h << 4) | (code); } while (0)
+#endif
 __device__ void traceback_service(const VitArgs& a)
 {
     const int lane = threadIdx.x & 31;
+    // phase word of this service warp (diagnostics): (ticket << 4) | what it is doing
+    volatile unsigned* const phase = a.slab_free + 2 * a.n_fwd + blockIdx.x * (VIT_THREADS / 32) + (threadIdx.x >> 5);
     for (;;)
     {
         unsigned h = 0;
         if (lane == 0) h = atomicAdd(a.tb_head, 1u);
         h = __shfl_sync(0xffffffffu, h, 0);
-        if (h >= a.n_jobs) return;
+        if (h >= a.n_jobs) { NC_SVC_PHASE(5u); return; }
+        NC_SVC_PHASE(1u);
         TbTicket& tk = a.tickets[h];
         const long long w0 = clock64();
         bool gave_up = false;
@@ -781,7 +826,8 @@ __device__ void traceback_service(const VitArgs& a)
                 if (ns < 2048) ns *= 2;
             }
         }
-        if (__shfl_sync(0xffffffffu, gave_up, 0)) return;
+        if (__shfl_sync(0xffffffffu, gave_up, 0)) { NC_SVC_PHASE(6u); return; }
+        NC_SVC_PHASE(2u);
         const long long w1 = clock64();
         unsigned passes = 0, steps = 0;
         const unsigned job_idx = __ldcg(&tk.job), slab_id = __ldcg(&tk.slab), final_state = __ldcg(&tk.final_state);
@@ -839,8 +885,11 @@ __device__ void traceback_service(const VitArgs& a)
         }
         __threadfence();   // states visible to the lanes that derive the moves; slab reads are complete
         __syncwarp();
+        NC_SVC_PHASE(3u);
         ca_free(reinterpret_cast< ColAlloc* >(a.colalloc), col0, n, lane, a.abort_word);
-        if (lane == 0) atomicAdd(a.slab_free + slab_id, 1u);   // slab_id = the forward CTA that ran the job
+        if (lane == 0) atomicAdd(a.slab_free + slab_id, 1u);
+        NC_SVC_PHASE(4u);
+        if (NC_SVC_ON && lane == 0 && ldv_abort(a.abort_word) != 0u) atomicAdd(a.slab_free + 2 * a.n_fwd + 64, 1u);   // releases after the abort   // slab_id = the forward CTA that ran the job
         if (a.stats)
         {
             for (int d = 16; d > 0; d >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, d);
@@ -880,6 +929,7 @@ void viterbi_alpha_colalloc_init(void* host_image, unsigned pool_columns)
     ColAlloc* A = static_cast< ColAlloc* >(host_image);
     memset(A, 0, sizeof(ColAlloc));
     A->n_free = 1;
+    A->max_free = pool_columns;
     A->start[0] = 0;
     A->len[0] = pool_columns;
 }

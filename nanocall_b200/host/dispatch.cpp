@@ -212,6 +212,7 @@ bool run_pipeline(const Run_Config& cfg, Read_Source& src, std::ostream* fasta, 
                         const auto i0 = Clock::now();
                         p.reset(new Pipeline(cfg.opt, cfg.devices[g], hint));
                         p->init_models();
+                        p->init_transitions();
                         ds.init_s = secs(i0, Clock::now());
                     }
                     if (!first_batch_seen.exchange(true))

@@ -170,6 +170,44 @@ void Pipeline::init_models()
     if (models_.empty()) throw std::runtime_error("no builtin models found for pore [" + opt_.pore + "]");
 }
 
+// init_transitions (nanocall.cpp:180-193): a custom initial table (-s/--trans, State_Transitions::operator>>,
+// State_Transitions.hpp:237-252: lines "kmer_i kmer_j log_prob", kept in file order), or the parametric one
+void Pipeline::init_transitions()
+{
+    if (opt_.trans_fn.empty())
+    {
+        NLOG(2, "init_state_transitions pr_skip=[" << opt_.pr_skip << "], pr_stay=[" << opt_.pr_stay << "]");
+        return;
+    }
+    std::ifstream is(opt_.trans_fn);
+    if (!is) throw std::runtime_error("cannot open " + opt_.trans_fn);
+    auto to_int = [&](const std::string& s) {
+        if (s.size() != NC_KMER) throw std::runtime_error("bad k-mer [" + s + "] in " + opt_.trans_fn);
+        unsigned idx = 0;
+        for (char c : s)
+        {
+            int b = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+            if (b < 0) throw std::runtime_error("bad base in " + opt_.trans_fn);
+            idx = (idx << 2) | (unsigned)b;
+        }
+        return (uint16_t)idx;
+    };
+    std::vector< uint16_t > from, to;
+    std::vector< float > lp;
+    std::string ki, kj;
+    float p;
+    while (is >> ki >> kj >> p)
+    {
+        from.push_back(to_int(ki));
+        to.push_back(to_int(kj));
+        lp.push_back(p);
+    }
+    if (from.empty()) throw std::runtime_error("no transitions in " + opt_.trans_fn);
+    check(nc_ctx_set_default_transitions(ctx_, opt_.pr_stay, opt_.pr_skip, (uint32_t)from.size(), from.data(), to.data(), lp.data()),
+          "nc_ctx_set_default_transitions");
+    NLOG(2, "loaded state transitions from [" << opt_.trans_fn << "]");
+}
+
 // ---------------------------------------------------------------- initial scaling (Fast5_Summary.hpp:210-278)
 void Pipeline::init_read_params(Read& r) const
 {

@@ -102,6 +102,7 @@ public:
     Pipeline& operator=(const Pipeline&) = delete;
 
     void init_models();
+    void init_transitions();
     void init_read_params(Read& r) const;
     void train_reads(std::vector< Read* >& reads);
     void basecall_reads(std::vector< Read* >& reads);

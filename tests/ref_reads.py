@@ -25,7 +25,32 @@ DATASETS = {
     "r73_opts": (107, [(60, 1500, 1300)], "r73", ["--pore", "r73", "--max-ed-events", "2500", "--trim-ed-sq-start", "30",
                                                    "--trim-ed-hp-end", "70", "--fasta-line-width", "60",
                                                    "--scaling-num-events", "120", "--scaling-max-rounds", "4"]),
+    # --trans: a custom initial transition table in the reference's file format, produced by the reference's own
+    # compute-state-transitions (full form with a probability cutoff: neighbour sets differ from the fast table's);
+    # in force while a strand's transition parameters are the defaults, i.e. in the first training round, and for
+    # the Viterbi pass as well when transitions are not trained
+    "r73_trans": (108, [(50, 900, 800)], "r73", ["--pore", "r73", "--trans", "@TRANS:-k,0.3,-t,0.1,-p,0.0005@"]),
+    "r73_trans_fixed": (109, [(40, 800, 700)], "r73", ["--pore", "r73", "--no-train-transitions", "--trans", "@TRANS:-k,0.25,-t,0.12,-p,0.002@"]),
 }
+
+CST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "compute_state_transitions")
+
+
+def materialize_options(opts, out_dir):
+    """Replace "@TRANS:<args>@" by the path of a transition table generated with the reference's tool (None if the tool
+    is not built)."""
+    out = []
+    for o in opts:
+        if o.startswith("@TRANS:"):
+            if not os.path.exists(CST):
+                return None
+            import subprocess
+            path = os.path.join(out_dir, "trans.tsv")
+            subprocess.run([CST] + o[7:-1].split(",") + ["-o", path], check=True)
+            out.append(path)
+        else:
+            out.append(o)
+    return out
 
 
 def write_inputs(name, out_dir):

@@ -133,3 +133,43 @@ def test_train_round_waves(ctx, port, models):
     for g in (0, 17, 39):
         exp = port.train_one_round(groups[g]["seqs"], table, table, groups[g]["pm"], groups[g]["st"])
         _check_round(got[g], exp, strands=(0,))
+
+
+def test_custom_transition_table_kernels_match_the_oracle(ctx, port, models):
+    """--trans: a table given as stored edges takes the list-walking kernels.  Fed with the edges of the parametric table
+    itself (the oracle's to_v lists, in order), Viterbi and Forward/Backward must reproduce the oracle bit for bit; fed
+    with the same edges in REVERSED file order, Viterbi's tie rule and the fold order follow the file."""
+    import numpy as np
+    from nanocall_b200 import api, synth
+    table = models["r73.t.006.ont.model"]["table"]
+    mid = ctx.register_model(table, 0)
+    tr = port.transitions(0.1, 0.3)
+    frm, to, lp = [], [], []
+    for i in range(4096):
+        for k in range(int(tr["to_cnt"][i])):
+            frm.append(i); to.append(int(tr["to_idx"][i, k])); lp.append(tr["to_lp"][i, k])
+    rng = np.random.default_rng(3)
+    pm = synth.random_params(rng, 1)[0]
+    rd = synth.make_read(rng, table, 300, tuple(pm))
+    try:
+        ctx.set_default_transitions(0.1, 0.3, frm, to, lp)
+        out = ctx.viterbi(np.array([0, 300], np.uint64), rd["mean"], rd["stdv"], rd["start"], mid, pm=pm)
+        exp = port.viterbi(table, pm, 0.1, 0.3, rd["mean"], rd["stdv"], rd["start"])
+        assert out["path_logprob"].view(np.uint32)[0] == np.float32(exp["path_prob"]).view(np.uint32)
+        assert np.array_equal(out["states"].astype(np.uint32), exp["states"])
+        assert np.array_equal(out["moves"].astype(np.int32), exp["moves"])
+        fb = ctx.forward_backward(mid, pm, (0.1, 0.3), rd["mean"][:60], rd["stdv"][:60], rd["start"][:60])
+        efb = port.fwbw(table, pm, 0.1, 0.3, rd["mean"][:60], rd["stdv"][:60], rd["start"][:60])
+        assert np.array_equal(fb["alpha"].view(np.uint32), efb["alpha"].view(np.uint32))
+        assert np.array_equal(fb["beta"].view(np.uint32), efb["beta"].view(np.uint32))
+        assert fb["log_pr_data"].view(np.uint32) == efb["log_pr_data"].view(np.uint32)
+        # other parameters than the defaults: the parametric kernels, untouched by the table
+        out2 = ctx.viterbi(np.array([0, 300], np.uint64), rd["mean"], rd["stdv"], rd["start"], mid, pm=pm, st=(0.12, 0.25))
+        exp2 = port.viterbi(table, pm, 0.12, 0.25, rd["mean"], rd["stdv"], rd["start"])
+        assert out2["path_logprob"].view(np.uint32)[0] == np.float32(exp2["path_prob"]).view(np.uint32)
+        # reversed file order: same Viterbi score (max is order-free), forward sums folded in another order
+        ctx.set_default_transitions(0.1, 0.3, frm[::-1], to[::-1], lp[::-1])
+        out3 = ctx.viterbi(np.array([0, 300], np.uint64), rd["mean"], rd["stdv"], rd["start"], mid, pm=pm)
+        assert out3["path_logprob"].view(np.uint32)[0] == np.float32(exp["path_prob"]).view(np.uint32)
+    finally:
+        ctx.set_default_transitions(0.1, 0.3)

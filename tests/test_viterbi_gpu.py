@@ -236,6 +236,39 @@ def test_column_allocator_under_pressure(port, models, vit_mode):
         c.close()
 
 
+def test_many_short_jobs_with_a_full_pool(models, vit_mode, monkeypatch):
+    """2000 jobs of 300-1400 events and a pool of 4 GiB: every forward CTA may hold five jobs, more than the pool has
+    columns for, so most forward CTAs wait for columns while the 48 service warps release them.  (With a
+    compare-and-swap lock on the extent list the waiting warps starved the service warps of the lock for minutes on
+    some GPUs; the list now has a FIFO lock and waiters that cannot fit do not take it.)  Must finish in well under the
+    10 s wait limit, three times in a row, with the same results as the backpointer kernel."""
+    if vit_mode != "alpha":
+        pytest.skip("runs once")
+    monkeypatch.setenv("NC_WAIT_LIMIT_S", "10")
+    from nanocall_b200 import _lib as L
+    import time
+    table = models[R73T]["table"]
+    rng = np.random.default_rng(77)
+    lengths = [int(v) for v in rng.integers(300, 1429, size=2000)]
+    batch = synth.make_batch(78, table, lengths)
+    for pool in (4 << 30, 1 << 30):
+        c = api.Context(0, bp_pool_bytes=pool)
+        try:
+            mid = c.register_model(table, 0)
+            c.set_viterbi_mode(L.NC_VIT_BACKPOINTER)
+            ref = c.viterbi(batch["ev_off"], batch["mean"], batch["stdv"], batch["start"], mid)
+            c.set_viterbi_mode(L.NC_VIT_AUTO)
+            for _ in range(3):
+                t0 = time.time()
+                out = c.viterbi(batch["ev_off"], batch["mean"], batch["stdv"], batch["start"], mid)
+                assert time.time() - t0 < 5.0
+                assert c.last_launches() == 1
+                assert np.array_equal(_bits(out["path_logprob"]), _bits(ref["path_logprob"]))
+                assert np.array_equal(out["states"], ref["states"]) and np.array_equal(out["moves"], ref["moves"])
+        finally:
+            c.close()
+
+
 def test_streamed_event_upload(port, models, vit_mode, monkeypatch):
     """Host-memory calls above a size threshold start the kernels first and stream the events behind them in chunks
     (jobs wait for their events to land).  Forced here on a small batch with 4096-event chunks: same bits."""

@@ -37,8 +37,9 @@ def main():
             fofn = os.path.join(d, "fofn.txt")
             open(fofn, "w").write("\n".join(files) + "\n")
             opts = ref_reads.DATASETS[name][3]
+            run_opts = ref_reads.materialize_options(opts, d)
             t0 = time.time()
-            p = subprocess.run([REF] + opts + ["-t", str(threads), "-o", os.path.join(d, "out.fa"), "--stats",
+            p = subprocess.run([REF] + run_opts + ["-t", str(threads), "-o", os.path.join(d, "out.fa"), "--stats",
                                                os.path.join(d, "stats.tsv"), fofn], capture_output=True, text=True)
             assert p.returncode == 0, p.stderr[-2000:]
             lines = [m.group(0) for m in (KEEP.search(l) for l in p.stderr.split("\n")) if m]
