@@ -334,29 +334,36 @@ struct ColAlloc
 };
 __device__ __forceinline__ unsigned ldv(const unsigned* p) { return *reinterpret_cast< const volatile unsigned* >(p); }
 __device__ __forceinline__ void stv(unsigned* p, unsigned v) { *reinterpret_cast< volatile unsigned* >(p) = v; }
-__device__ __forceinline__ void ca_lock(ColAlloc* A, int lane)
+// returns the ticket (lane 0), which ca_unlock hands on
+__device__ __forceinline__ unsigned ca_lock(ColAlloc* A, int lane)
 {
+    unsigned my = 0;
     if (lane == 0)
     {
-        const unsigned my = atomicAdd(&A->next_ticket, 1u);
+        my = atomicAdd(&A->next_ticket, 1u);
         for (;;)
         {
             const unsigned ahead = my - ld_acquire_u32(&A->now_serving);
             if (ahead == 0u) break;
-            __nanosleep(ahead > 16u ? 2048u : ahead * 128u);   // a turn lasts about a microsecond
+            if (ahead > 1u) __nanosleep(ahead > 16u ? 2048u : ahead * 128u);   // a turn lasts about a microsecond; next in line spins
         }
-        __threadfence();
     }
     __syncwarp();
+    return my;
 }
-__device__ __forceinline__ void ca_unlock(ColAlloc* A, int lane)
+__device__ __forceinline__ void ca_unlock(ColAlloc* A, int lane, unsigned my)
 {
     __syncwarp();
-    if (lane == 0)
-    {
-        __threadfence();
-        st_release_u32(&A->now_serving, ldv(&A->now_serving) + 1u);   // (only the holder writes it)
-    }
+    if (lane == 0) st_release_u32(&A->now_serving, my + 1u);   // release: the list writes of the whole warp (ordered before
+                                                               // this store by the warp barrier) are visible to the next holder
+}
+// n_free and max_free in one load
+__device__ __forceinline__ void ca_header(const ColAlloc* A, unsigned& n_free, unsigned& max_free)
+{
+    unsigned t0, t1;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(n_free), "=r"(max_free) : "l"(A) : "memory");
+    (void)t0; (void)t1;
+    (void)t0; (void)t1;
 }
 // remove entry `at` of a list of nf entries (called with the lock held, by the whole warp)
 __device__ __forceinline__ void ca_remove(ColAlloc* A, unsigned at, unsigned nf, int lane)
@@ -372,20 +379,41 @@ __device__ __forceinline__ void ca_remove(ColAlloc* A, unsigned at, unsigned nf,
     }
     if (lane == 0) stv(&A->n_free, nf - 1);
 }
+// Lists of at most 32 extents (the usual case) are handled in registers: the header and one entry per lane arrive in one
+// round trip to L2, neighbours come from shuffles, and the holder only issues stores before it passes the lock on.  With
+// short reads the two list operations per job are what bounds the kernel, so the time under the lock matters.
+//
 // n columns, first fit; false when no extent is large enough right now
 __device__ __forceinline__ bool ca_alloc(ColAlloc* A, unsigned n, unsigned& s, int lane)
 {
-    ca_lock(A, lane);
-    const unsigned nf = ldv(&A->n_free);
+    const unsigned my = ca_lock(A, lane);
+    unsigned nf, bound;
+    ca_header(A, nf, bound);
+    unsigned l = ldv(A->len + lane), st = ldv(A->start + lane);   // (entries past nf are stale: masked below)
     int found = -1;
-    unsigned longest = 0;
+    unsigned longest = 0, l_found = 0, s_found = 0;
     for (unsigned base = 0; base < nf; base += 32)
     {
         const unsigned i = base + lane;
-        const unsigned l = (i < nf) ? ldv(A->len + i) : 0u;
+        if (base) { l = ldv(A->len + i); st = ldv(A->start + i); }
+        if (i >= nf) l = 0u;
         longest = l > longest ? l : longest;
         const unsigned m = __ballot_sync(0xffffffffu, l >= n);
-        if (m) { found = (int)base + __ffs(m) - 1; break; }
+        if (m)
+        {
+            const int src = __ffs(m) - 1;
+            found = (int)base + src;
+            l_found = __shfl_sync(0xffffffffu, l, src);
+            s_found = __shfl_sync(0xffffffffu, st, src);
+            if (l_found == n && nf <= 32u)
+            {
+                // the extent is used up: entries above it move down by one (register copy of the only chunk)
+                const unsigned st_up = __shfl_down_sync(0xffffffffu, st, 1), l_up = __shfl_down_sync(0xffffffffu, l, 1);
+                if (lane >= src && (unsigned)lane + 1u < nf) { stv(A->start + lane, st_up); stv(A->len + lane, l_up); }
+                if (lane == 0) stv(&A->n_free, nf - 1u);
+            }
+            break;
+        }
     }
     if (found < 0)
     {
@@ -393,75 +421,109 @@ __device__ __forceinline__ bool ca_alloc(ColAlloc* A, unsigned n, unsigned& s, i
         longest = __reduce_max_sync(0xffffffffu, longest);
         if (lane == 0) stv(&A->max_free, longest);
     }
-    if (found >= 0)
+    else
     {
-        const unsigned l = ldv(A->len + found), s0 = ldv(A->start + found);
-        s = s0;
-        __syncwarp();
-        if (l > n)
+        s = s_found;
+        if (l_found > n)
         {
-            if (lane == 0) { stv(A->start + found, s0 + n); stv(A->len + found, l - n); }
+            if (lane == 0) { stv(A->start + found, s_found + n); stv(A->len + found, l_found - n); }
         }
-        else ca_remove(A, (unsigned)found, nf, lane);
+        else if (nf > 32u) ca_remove(A, (unsigned)found, nf, lane);
     }
-    ca_unlock(A, lane);
+    ca_unlock(A, lane, my);
     return found >= 0;
 }
 __device__ __forceinline__ void ca_free(ColAlloc* A, unsigned s, unsigned n, int lane, unsigned* abort_word)
 {
-    ca_lock(A, lane);
-    const unsigned nf = ldv(&A->n_free);
-    unsigned idx = 0;   // number of extents below s = position of the released extent
-    for (unsigned base = 0; base < nf; base += 32)
-    {
-        const unsigned i = base + lane;
-        const unsigned m = __ballot_sync(0xffffffffu, i < nf && ldv(A->start + i) < s);
-        idx += __popc(m);
-        if (m != 0xffffffffu) break;
-    }
-    const bool join_prev = idx > 0 && ldv(A->start + idx - 1) + ldv(A->len + idx - 1) == s;
-    const bool join_next = idx < nf && s + n == ldv(A->start + idx);
-    __syncwarp();
+    const unsigned my = ca_lock(A, lane);
+    unsigned nf, bound;
+    ca_header(A, nf, bound);
     unsigned merged = n;   // length of the free extent that now holds the released columns
-    if (join_prev && join_next)
+    if (nf <= 32u)
     {
-        merged = n + ldv(A->len + idx) + ldv(A->len + idx - 1);
-        __syncwarp();
-        if (lane == 0) stv(A->len + idx - 1, merged);
-        ca_remove(A, idx, nf, lane);
-    }
-    else if (join_prev)
-    {
-        merged = ldv(A->len + idx - 1) + n;
-        __syncwarp();
-        if (lane == 0) stv(A->len + idx - 1, merged);
-    }
-    else if (join_next)
-    {
-        merged = ldv(A->len + idx) + n;
-        __syncwarp();
-        if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, merged); }
-    }
-    else if (nf < (unsigned)CA_MAX)
-    {
-        // insert at idx: move entries idx..nf-1 up by one, top chunk first
-        for (unsigned hi = nf; hi > idx;)
+        const unsigned st = ldv(A->start + lane), l = ldv(A->len + lane);
+        const unsigned idx = (unsigned)__popc(__ballot_sync(0xffffffffu, (unsigned)lane < nf && st < s));   // extents below s
+        const unsigned prev_st = __shfl_sync(0xffffffffu, st, (int)((idx + 31u) & 31u)), prev_l = __shfl_sync(0xffffffffu, l, (int)((idx + 31u) & 31u));
+        const unsigned next_st = __shfl_sync(0xffffffffu, st, (int)(idx & 31u)), next_l = __shfl_sync(0xffffffffu, l, (int)(idx & 31u));
+        const bool join_prev = idx > 0u && prev_st + prev_l == s;
+        const bool join_next = idx < nf && s + n == next_st;
+        if (join_prev && join_next)
         {
-            const unsigned lo = (hi - idx > 32u) ? hi - 32u : idx;
-            const unsigned i = lo + lane;
-            const bool have = i < hi;
-            const unsigned st = have ? ldv(A->start + i) : 0u, ln = have ? ldv(A->len + i) : 0u;
-            __syncwarp();
-            if (have) { stv(A->start + i + 1, st); stv(A->len + i + 1, ln); }
-            __syncwarp();
-            hi = lo;
+            merged = prev_l + n + next_l;
+            const unsigned st_up = __shfl_down_sync(0xffffffffu, st, 1), l_up = __shfl_down_sync(0xffffffffu, l, 1);
+            if ((unsigned)lane >= idx && (unsigned)lane + 1u < nf) { stv(A->start + lane, st_up); stv(A->len + lane, l_up); }
+            if (lane == 0) { stv(A->len + idx - 1u, merged); stv(&A->n_free, nf - 1u); }
         }
-        if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, n); stv(&A->n_free, nf + 1); }
+        else if (join_prev)
+        {
+            merged = prev_l + n;
+            if (lane == 0) stv(A->len + idx - 1u, merged);
+        }
+        else if (join_next)
+        {
+            merged = next_l + n;
+            if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, merged); }
+        }
+        else
+        {
+            // insert at idx: entries idx..nf-1 move up by one (nf = 32 writes entry 32: the list has room for CA_MAX)
+            if ((unsigned)lane >= idx && (unsigned)lane < nf) { stv(A->start + lane + 1, st); stv(A->len + lane + 1, l); }
+            if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, n); stv(&A->n_free, nf + 1u); }
+        }
     }
-    else if (lane == 0) atomicCAS(abort_word, 0u, 4u);   // extent list full: an error, not a silent leak (the host also
-                                                         // refuses launches whose live jobs could exceed the list)
-    if (lane == 0 && merged > ldv(&A->max_free)) stv(&A->max_free, merged);
-    ca_unlock(A, lane);
+    else
+    {
+        unsigned idx = 0;   // number of extents below s = position of the released extent
+        for (unsigned base = 0; base < nf; base += 32)
+        {
+            const unsigned i = base + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, i < nf && ldv(A->start + i) < s);
+            idx += __popc(m);
+            if (m != 0xffffffffu) break;
+        }
+        const bool join_prev = idx > 0 && ldv(A->start + idx - 1) + ldv(A->len + idx - 1) == s;
+        const bool join_next = idx < nf && s + n == ldv(A->start + idx);
+        __syncwarp();
+        if (join_prev && join_next)
+        {
+            merged = n + ldv(A->len + idx) + ldv(A->len + idx - 1);
+            __syncwarp();
+            if (lane == 0) stv(A->len + idx - 1, merged);
+            ca_remove(A, idx, nf, lane);
+        }
+        else if (join_prev)
+        {
+            merged = ldv(A->len + idx - 1) + n;
+            __syncwarp();
+            if (lane == 0) stv(A->len + idx - 1, merged);
+        }
+        else if (join_next)
+        {
+            merged = ldv(A->len + idx) + n;
+            __syncwarp();
+            if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, merged); }
+        }
+        else if (nf < (unsigned)CA_MAX)
+        {
+            // insert at idx: move entries idx..nf-1 up by one, top chunk first
+            for (unsigned hi = nf; hi > idx;)
+            {
+                const unsigned lo = (hi - idx > 32u) ? hi - 32u : idx;
+                const unsigned i = lo + lane;
+                const bool have = i < hi;
+                const unsigned st = have ? ldv(A->start + i) : 0u, ln = have ? ldv(A->len + i) : 0u;
+                __syncwarp();
+                if (have) { stv(A->start + i + 1, st); stv(A->len + i + 1, ln); }
+                __syncwarp();
+                hi = lo;
+            }
+            if (lane == 0) { stv(A->start + idx, s); stv(A->len + idx, n); stv(&A->n_free, nf + 1); }
+        }
+        else if (lane == 0) atomicCAS(abort_word, 0u, 4u);   // extent list full: an error, not a silent leak (the host also
+                                                             // refuses launches whose live jobs could exceed the list)
+    }
+    if (lane == 0 && merged > bound) stv(&A->max_free, merged);
+    ca_unlock(A, lane, my);
 }
 
 // phase word of a forward CTA (diagnostics of an aborted grid): (jobs finished << 4) | what it is doing

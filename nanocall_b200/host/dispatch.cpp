@@ -207,8 +207,9 @@ bool run_pipeline(const Run_Config& cfg, Read_Source& src, std::ostream* fasta, 
                     if (!p)
                     {
                         // Viterbi scratch: what the jobs in flight of a batch like this one can use (two candidate
-                        // models per strand at most, ~300 jobs of the longest strand), unless the caller fixed it
-                        size_t hint = cfg.pool_bytes ? cfg.pool_bytes / 16384u : std::min(2 * ev, 300 * std::max< size_t >(longest, 1));
+                        // models per strand at most; every forward CTA holds up to five jobs: ~760 jobs of the longest
+                        // strand), unless the caller fixed it
+                        size_t hint = cfg.pool_bytes ? cfg.pool_bytes / 16384u : std::min(2 * ev, 760 * std::max< size_t >(longest, 1));
                         const auto i0 = Clock::now();
                         p.reset(new Pipeline(cfg.opt, cfg.devices[g], hint));
                         p->init_models();
