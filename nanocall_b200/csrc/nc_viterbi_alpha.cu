@@ -360,10 +360,7 @@ __device__ __forceinline__ void ca_unlock(ColAlloc* A, int lane, unsigned my)
 // n_free and max_free in one load
 __device__ __forceinline__ void ca_header(const ColAlloc* A, unsigned& n_free, unsigned& max_free)
 {
-    unsigned t0, t1;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(n_free), "=r"(max_free) : "l"(A) : "memory");
-    (void)t0; (void)t1;
-    (void)t0; (void)t1;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(n_free), "=r"(max_free) : "l"(&A->n_free) : "memory");
 }
 // remove entry `at` of a list of nf entries (called with the lock held, by the whole warp)
 __device__ __forceinline__ void ca_remove(ColAlloc* A, unsigned at, unsigned nf, int lane)
