@@ -74,6 +74,18 @@ __device__ __forceinline__ float fold_logsum_in_order(float acc, const int n, Ge
 // a + t is the result; otherwise the recomputed indices are the next guess (the first unconfirmed lane is certainly
 // right then).  After three rounds, or when a term exceeds the running value (start of a chain), the block is folded
 // term by term.  lst: 40 floats, 16-byte aligned, private to the warp.
+#ifndef NC_ST_EXP
+#define NC_ST_EXP 0   // timing experiments only: 1 = no phase-2 arithmetic, 2 = no fold; anything but 0 is not a product build
+#endif
+#ifndef NC_ST_PRE
+#define NC_ST_PRE 1
+#endif
+#if NC_ST_EXP == 9
+__device__ unsigned long long g_dbg[8];   // blocks, speculative blocks, exact rounds, sequential fallbacks, live items
+#define FOLD_DBG(k, v) do { if (lane == 0) atomicAdd(&g_dbg[k], (unsigned long long)(v)); } while (0)
+#else
+#define FOLD_DBG(k, v) do { } while (0)
+#endif
 template < typename TB >
 __device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl, const int lane, float* __restrict__ lst)
 {
@@ -81,16 +93,37 @@ __device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl,
     const unsigned m = __ballot_sync(FULL, live);
     if (m == 0) return acc;
     const bool spec_ok = __all_sync(FULL, !live || acc >= x);   // (false for acc == -inf with a finite term, and for NaN)
+    FOLD_DBG(0, 1); FOLD_DBG(4, __popc(m));
     if (spec_ok)
     {
+        FOLD_DBG(1, 1);
         const float INF = __int_as_float(0x7f800000);   // dead lanes: d = +inf selects the zero entry
         const int L = __popc(m);
         const int r = __popc(m & ((1u << lane) - 1u));   // live terms below this lane
         const int last = 31 - __clz((int)m);
         unsigned e = tbl.addr(live ? __fsub_rn(acc, x) : INF);
+        // A cheap refinement of the guess before the exact chain (NC_ST_PRE of them; measured: 1.75 exact rounds per block
+        // without, 1.04 with one, 1.006 with two, and one is the fastest): a parallel prefix of the increments (rounded
+        // differently from the sequential sum, which only matters within an ulp of an index boundary) gives every lane an
+        // estimate of its running value and with it a better index.  The exact rounds below verify whatever comes out.
+#pragma unroll
+        for (int pre = 0; pre < NC_ST_PRE; ++pre)
+        {
+            float p = live ? tbl.load(e) : 0.0f;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const float v = __shfl_up_sync(FULL, p, d);
+                if (lane >= d) p = __fadd_rn(p, v);
+            }
+            const float before = __shfl_up_sync(FULL, p, 1);                  // increments of the lanes below
+            const float est = __fadd_rn(acc, lane ? before : 0.0f);
+            e = tbl.addr(live ? fmaxf(__fsub_rn(est, x), 0.0f) : INF);
+        }
 #pragma unroll 1
         for (int round = 0; round < 3; ++round)
         {
+            FOLD_DBG(2, 1);
             const float t = tbl.load(e);
             if (live) lst[r] = t;
             if (lane < 8) lst[L + lane] = 0.0f;
@@ -100,11 +133,11 @@ __device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl,
             for (int k = 0; k < L; k += 4)
             {
                 // the next four increments are fetched before these are added: the chain of FADDs never waits for a load
+                // (a lane stops at its own position by adding zeros: the selects are off the chain, which is FADD after FADD)
                 const float4 vn = *reinterpret_cast< const float4* >(lst + k + 4);
-                a = (k + 0 < r) ? __fadd_rn(a, v.x) : a;
-                a = (k + 1 < r) ? __fadd_rn(a, v.y) : a;
-                a = (k + 2 < r) ? __fadd_rn(a, v.z) : a;
-                a = (k + 3 < r) ? __fadd_rn(a, v.w) : a;
+                const float t0 = (k + 0 < r) ? v.x : 0.0f, t1 = (k + 1 < r) ? v.y : 0.0f;
+                const float t2 = (k + 2 < r) ? v.z : 0.0f, t3 = (k + 3 < r) ? v.w : 0.0f;
+                a = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a, t0), t1), t2), t3);
                 v = vn;
             }
             __syncwarp();
@@ -114,6 +147,7 @@ __device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl,
             e = e2;
         }
     }
+    FOLD_DBG(3, 1);
     for (unsigned mm = m; mm; mm &= mm - 1)
     {
         const int k = __ffs(mm) - 1;
@@ -131,18 +165,28 @@ struct FbSmem
     unsigned item;
 };
 
-constexpr int ST_PROD = FB_THREADS - 3 * 32;   // 416 producer threads of st_stats_kernel (13 warps)
-constexpr int ST_R = 6;                        // training k-mers per producer thread and event (6 x 416 >= 2160)
-constexpr int ST_P2 = 256;                     // live (event, k-mer) items per hand-over to the fold warps
-constexpr unsigned ST_DONE = 0xffffffffu;
+// st_stats_kernel's geometry.  The three fold warps of a CTA run dependent chains and every producer warp is a chain of
+// memory latencies, so what counts is how many of them are in flight: CTAs of 256 threads (3 fold warps + 5 producer
+// warps, each producer warp working on its own event), six per SM, the p7_FLogsum table read through L1 instead of
+// 64 KB of shared memory per CTA.
+constexpr int ST_THREADS = 256;
+constexpr int ST_CTAS = 6;
+constexpr int ST_PW = ST_THREADS / 32 - 3;     // producer warps
+constexpr int ST_CH = 68;                      // training k-mers per lane and event (68 x 32 >= 2160), in 32-wide chunks
+constexpr int ST_LIST = 512;                   // live items a producer warp lists at a time
+constexpr int ST_RING = 1024;                  // items between the producers and the slowest fold warp (several events)
 struct StSmem
 {
-    float tbl[fb::TBL_N];
-    float term[2][3][ST_P2];      // two hand-over buffers: terms of live items, in order
-    unsigned cnt[2];              // items in each buffer (ST_DONE: no more hand-overs)
-    unsigned short live[ST_R * ST_PROD];   // positions (in the training k-mer list) of the event's live items, ascending
-    unsigned wtot[13];            // live items per producer warp
-    float acc_snap[4];            // running values the fold warps published after their last hand-over
+    float ring[3][ST_RING];       // terms of the live items, in order, one ring per accumulator (slot = item index mod ST_RING)
+    unsigned short list[ST_PW][ST_LIST];   // per producer warp: positions (in the training k-mer list) of live items, ascending
+    unsigned e_claim;             // next event to hand to a producer warp
+    unsigned e_counted;           // events whose live items have been counted (their item offsets are fixed)
+    unsigned n_counted;           // live items of those events
+    unsigned e_pub;               // events completely published
+    unsigned pub;                 // items published so far (a prefix of the item sequence)
+    unsigned done;                // set after the last publication
+    unsigned cons[4];             // items consumed by each fold warp
+    float acc_snap[4];            // running values the fold warps published last
     __align__(16) float lst[3][40];   // fold32's warp-private lists
     unsigned seq_id[NC_MAX_TRAIN_SEQS];      // the strand's sequences with >= 2 events, in order
     unsigned seq_first[NC_MAX_TRAIN_SEQS + 1];  // first flattened (event) index of each
@@ -326,6 +370,8 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
 
 size_t fwbw_smem_bytes() { return sizeof(FbSmem); }
 size_t st_stats_smem_bytes() { return sizeof(StSmem); }
+unsigned st_stats_threads() { return ST_THREADS; }
+unsigned st_stats_max_kmers() { return ST_CH * 32; }
 
 // ------------------------------------------------------------------------------------------------
 // train_pm_params' inner sums (Parameter_Trainer.hpp:263-296): per event
@@ -446,15 +492,34 @@ size_t pm_stats_smem_bytes() { return (size_t)2 * PM_JT * PM_ROW * sizeof(float)
 // (events x 2160) terms per accumulator, (+) = p7_FLogsum.
 //
 // A term more than 15.999 below the running value leaves it unchanged, and the three terms of a k-mer are bounded by its
-// log posterior (stay and skip are clamped to it; log(exp(.)) round trips stay within a few ulps).  So per event:
-//   phase 1  (13 producer warps, 6 k-mers per thread)  log posterior of every training k-mer, two loads each; a k-mer
-//            whose log posterior is 16.25 below the smallest of the three running values the fold warps last published
-//            (stale values are smaller, hence conservative) is dead for all three chains; the others are compacted, in
-//            order, into a list -- typically a tenth of the k-mers;
-//   phase 2  the full terms (five joint probabilities, p7_FLogsum, two expf, one logf) of the listed k-mers only, at
-//            most 256 per hand-over, into one of two buffers;
-//   fold     warps 0..2, one accumulator each, absorb the previous hand-over 32 terms per step (fold32) meanwhile.
-__global__ void __launch_bounds__(FB_THREADS, 3) st_stats_kernel(const FbArgs a)
+// log posterior (stay and skip are clamped to it; log(exp(.)) round trips stay within a few ulps).  Only the fold is
+// sequential; which items can matter, and their terms, can be worked out for several events at once:
+//   producer warps  each takes the next event: (1) log posterior of every training k-mer, two loads each; a k-mer whose
+//            log posterior is 16.25 below the smallest of the three running values the fold warps last published (stale
+//            values are smaller, hence conservative) is dead for all three chains: one flag bit per k-mer, in registers;
+//            (2) the number of live items fixes where the event's items go in the item sequence, once the events before
+//            it are counted (e_counted / n_counted, in event order); (3) the full terms (five joint probabilities,
+//            p7_FLogsum, two expf, one logf) of the live k-mers only -- typically a tenth -- 32 at a time into the rings;
+//            (4) publication in event order (the warp whose event is the oldest unpublished one also publishes its
+//            partial progress, so an event with more live items than the ring holds cannot block).
+//   fold warps      one accumulator each, absorb the published items 32 per step (fold32) as they come.
+// A chain of 200 events took 3.4 ms when the producers handled one event at a time (every event a chain of three DRAM
+// latencies); the kernel's time is that latency times the number of CTA rounds of a wave.
+// loads of the alpha / beta / emission rows: each is used once or twice, so they must not push the p7_FLogsum table
+// (read through L1 by the fold warps, whose chain waits for every lookup) out of the cache
+__device__ __forceinline__ float ld_stream(const float* p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_stream4(const float* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__global__ void __launch_bounds__(ST_THREADS, ST_CTAS) st_stats_kernel(const FbArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StSmem& ss = *reinterpret_cast< StSmem* >(smem_raw);
@@ -462,7 +527,6 @@ __global__ void __launch_bounds__(FB_THREADS, 3) st_stats_kernel(const FbArgs a)
     const unsigned grp = blockIdx.x;
     const unsigned st = blockIdx.y;
     const FbGroup& G = a.groups[grp];
-    for (int q = t; q < fb::TBL_N; q += FB_THREADS) ss.tbl[q] = a.logsum_tbl[q];
     if (t == 0)
     {
         unsigned ns = 0, first = 0;
@@ -476,24 +540,45 @@ __global__ void __launch_bounds__(FB_THREADS, 3) st_stats_kernel(const FbArgs a)
             }
         ss.seq_first[ns] = first;
         ss.n_seq = ns;
+        ss.e_claim = ss.e_counted = ss.n_counted = ss.e_pub = ss.pub = ss.done = 0u;
     }
-    if (t < 4) ss.acc_snap[t] = NC_NEG_INF;
+    if (t < 4) { ss.acc_snap[t] = NC_NEG_INF; ss.cons[t] = 0u; }
     __syncthreads();
-    const fb::TblSmem tbl = fb::make_tbl_smem(ss.tbl);
-    const unsigned n_km = a.n_train_kmers;   // <= ST_R * ST_PROD (checked on the host)
+    fb::TblPtr tbl;
+    tbl.p = a.logsum_tbl;
+    const unsigned n_km = a.n_train_kmers;   // <= 32 ST_CH (checked on the host)
     const unsigned n_seq = ss.n_seq;
     const unsigned n_ev = ss.seq_first[n_seq];
+    volatile unsigned* const v_pub = &ss.pub;
+    volatile unsigned* const v_done = &ss.done;
+    volatile unsigned* const v_cons = ss.cons;
+    volatile float* const v_snap = ss.acc_snap;
+    volatile unsigned* const v_e_counted = &ss.e_counted;
+    volatile unsigned* const v_n_counted = &ss.n_counted;
+    volatile unsigned* const v_e_pub = &ss.e_pub;
 
     if (warp >= 3)
     {
-        // ================================================= producers
-        const int pt = t - 3 * 32, pw = warp - 3;
+        // ================================================= producer warps, one event each at a time
+        const int pw = warp - 3;
         const float log_p_stay = G.log_p_stay[st];
         const float log_p_step_4 = G.log_p_step_4[st];
-        int buf = 0;
-        unsigned s = 0;
-        for (unsigned ef = 0; ef < n_ev; ++ef)
+        unsigned short* const list = ss.list[pw];
+        const unsigned lt = (1u << lane) - 1u;
+        if (n_ev == 0 && pw == 0 && lane == 0) *v_done = 1u;
+#if NC_ST_EXP == 9
+        long long tk[6] = { 0, 0, 0, 0, 0, 0 }; long long t_prev = clock64(); unsigned n_items_dbg = 0, n_ev_dbg = 0;
+#define ST_TICK(k) do { const long long _n = clock64(); tk[k] += _n - t_prev; t_prev = _n; } while (0)
+#else
+#define ST_TICK(k) do { } while (0)
+#endif
+        for (;;)
         {
+            unsigned ef = 0;
+            if (lane == 0) ef = atomicAdd(&ss.e_claim, 1u);
+            ef = __shfl_sync(FULL, ef, 0);
+            if (ef >= n_ev) break;
+            unsigned s = 0;
             while (s + 1 < n_seq && ef >= ss.seq_first[s + 1]) ++s;
             const unsigned sq = ss.seq_id[s], i = ef - ss.seq_first[s];
             const FbSeq& Q = a.seqs[sq];
@@ -506,111 +591,207 @@ __global__ void __launch_bounds__(FB_THREADS, 3) st_stats_kernel(const FbArgs a)
             const float* Bi = BE + (size_t)i * NC_N_STATES;
             const float* Bn = BE + (size_t)(i + 1) * NC_N_STATES;
             const float* En = E + (size_t)(i + 1) * NC_N_STATES;
-            // ---- phase 1
-            const float smin = fminf(fminf(ss.acc_snap[0], ss.acc_snap[1]), ss.acc_snap[2]);
-            float av[ST_R], bv[ST_R];
-#pragma unroll
-            for (int r = 0; r < ST_R; ++r)
+            // ---- (1) which k-mers are live: lane l looks at k-mers 32 c + l, flag bit c
+            const float smin = fminf(fminf(v_snap[0], v_snap[1]), v_snap[2]);
+            unsigned long long flo = 0ull;   // flag bits of chunks 0..63
+            unsigned fhi = 0u;               // ... 64..67
+            unsigned mine = 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < ST_CH; c0 += 8)
             {
-                const unsigned km = (unsigned)(ST_R * pt + r);
-                if (km < n_km)
+                float av[8], bv[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
                 {
-                    const unsigned j1 = __ldg(a.train_kmers + km);
-                    av[r] = __ldg(Ai + j1);
-                    bv[r] = __ldg(Bi + j1);
-                }
-                else av[r] = bv[r] = NC_NEG_INF;
-            }
-            unsigned flags = 0;
-#pragma unroll
-            for (int r = 0; r < ST_R; ++r)
-            {
-                const float lp = __fsub_rn(__fadd_rn(av[r], bv[r]), logz);
-                const bool live = !((lp == NC_NEG_INF) || (smin > lp && __fsub_rn(smin, lp) >= 16.25f));
-                flags |= live ? (1u << r) : 0u;
-            }
-            const unsigned mine = __popc(flags);
-            unsigned incl = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1)
-            {
-                const unsigned v = __shfl_up_sync(FULL, incl, d);
-                if (lane >= d) incl += v;
-            }
-            if (lane == 31) ss.wtot[pw] = incl;
-            asm volatile("bar.sync 1, 416;" ::: "memory");
-            unsigned wbase = 0, n_live = 0;
-#pragma unroll
-            for (int w = 0; w < 13; ++w)
-            {
-                const unsigned c = ss.wtot[w];
-                wbase += (w < pw) ? c : 0u;
-                n_live += c;
-            }
-            {
-                unsigned pos = wbase + incl - mine;
-#pragma unroll
-                for (int r = 0; r < ST_R; ++r)
-                    if (flags & (1u << r)) ss.live[pos++] = (unsigned short)(ST_R * pt + r);
-            }
-            asm volatile("bar.sync 1, 416;" ::: "memory");
-            // ---- phase 2
-            for (unsigned b0 = 0; b0 < n_live; b0 += ST_P2)
-            {
-                const unsigned q = b0 + (unsigned)pt;
-                if (pt < ST_P2 && q < n_live)
-                {
-                    const unsigned j1 = __ldg(a.train_kmers + ss.live[q]);
-                    const unsigned nb = (j1 & 1023u) << 2;   // the four one-step successors are one aligned float4
-                    const float al = __ldg(Ai + j1), bi = __ldg(Bi + j1), en = __ldg(En + j1), bn = __ldg(Bn + j1);
-                    const float4 e4 = __ldg(reinterpret_cast< const float4* >(En + nb));
-                    const float4 b4 = __ldg(reinterpret_cast< const float4* >(Bn + nb));
-                    const float log_p_j1 = __fsub_rn(__fadd_rn(al, bi), logz);
-                    // joint(i, j1, j2, lt) = alpha + lt + emission(j2, e_{i+1}) + beta(i+1, j2) - logZ   (:457-469)
-                    float jj = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_stay), en), bn), logz);
-                    if (jj > log_p_j1) jj = log_p_j1;
-                    float s2 = flogsum(NC_NEG_INF, jj, tbl);
-                    const float ev[4] = { e4.x, e4.y, e4.z, e4.w }, bv4[4] = { b4.x, b4.y, b4.z, b4.w };
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
+                    const unsigned km = (unsigned)(32 * (c0 + r) + lane);
+                    if (c0 + r < ST_CH && km < n_km)
                     {
-                        const float jv = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_step_4), ev[b]), bv4[b]), logz);
-                        s2 = flogsum(s2, jv, tbl);
+                        const unsigned j1 = __ldg(a.train_kmers + km);
+                        av[r] = ld_stream(Ai + j1);
+                        bv[r] = ld_stream(Bi + j1);
                     }
-                    if (s2 > log_p_j1) s2 = log_p_j1;
-                    const float p2 = __fsub_rn(nc_expf(log_p_j1), nc_expf(s2));
-                    ss.term[buf][0][pt] = log_p_j1;
-                    ss.term[buf][1][pt] = jj;
-                    ss.term[buf][2][pt] = nc_logf(p2);
+                    else av[r] = bv[r] = NC_NEG_INF;
                 }
-                if (pt == 0) ss.cnt[buf] = min((unsigned)ST_P2, n_live - b0);
-                __syncthreads();   // hand-over (the fold warps wait here too)
-                buf ^= 1;
+                unsigned f8 = 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                {
+                    const float lp = __fsub_rn(__fadd_rn(av[r], bv[r]), logz);
+                    const bool live = !((lp == NC_NEG_INF) || (smin > lp && __fsub_rn(smin, lp) >= 16.25f));
+                    f8 |= live ? (1u << r) : 0u;
+                }
+                mine += __popc(f8);
+                if (c0 < 64) flo |= (unsigned long long)f8 << c0;
+                else fhi |= f8;
             }
+            const unsigned n_live = __reduce_add_sync(FULL, mine);
+            ST_TICK(0);
+            // ---- (2) the event's place in the item sequence
+            unsigned base = 0;
+            if (lane == 0)
+            {
+                while (*v_e_counted != ef) __nanosleep(100);
+                __threadfence_block();
+                base = *v_n_counted;
+                *v_n_counted = base + n_live;
+                __threadfence_block();
+                *v_e_counted = ef + 1u;
+            }
+            base = __shfl_sync(FULL, base, 0);
+            ST_TICK(1);
+            // ---- (3) the terms of the live k-mers, ST_LIST listed at a time
+            unsigned written = 0;
+            int c = 0;
+            while (written < n_live)
+            {
+                unsigned cnt = 0;
+                for (; c < ST_CH && cnt + 32u <= (unsigned)ST_LIST; ++c)
+                {
+                    const bool f = (c < 64) ? ((flo >> c) & 1ull) != 0ull : ((fhi >> (c - 64)) & 1u) != 0u;
+                    const unsigned m = __ballot_sync(FULL, f);
+                    if (f) list[cnt + __popc(m & lt)] = (unsigned short)(32 * c + lane);
+                    cnt += __popc(m);
+                }
+                __syncwarp();
+                for (unsigned b0 = 0; b0 < cnt; b0 += 32)
+                {
+                    const unsigned q = b0 + (unsigned)lane;
+                    if (q < cnt)
+                    {
+                        const unsigned j1 = __ldg(a.train_kmers + list[q]);
+                        const unsigned nb = (j1 & 1023u) << 2;   // the four one-step successors are one aligned float4
+                        const float al = ld_stream(Ai + j1), bi = ld_stream(Bi + j1), en = ld_stream(En + j1), bn = ld_stream(Bn + j1);
+                        const float4 e4 = ld_stream4(En + nb);
+                        const float4 b4 = ld_stream4(Bn + nb);
+                        const float log_p_j1 = __fsub_rn(__fadd_rn(al, bi), logz);
+                        float jj, t2;
+#if NC_ST_EXP == 1
+                        jj = log_p_j1 + (en + bn + e4.x + b4.x) * 0.0f;
+                        t2 = jj;
+#else
+                        // joint(i, j1, j2, lt) = alpha + lt + emission(j2, e_{i+1}) + beta(i+1, j2) - logZ   (:457-469)
+                        jj = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_stay), en), bn), logz);
+                        if (jj > log_p_j1) jj = log_p_j1;
+                        float s2 = flogsum(NC_NEG_INF, jj, tbl);
+                        const float ev[4] = { e4.x, e4.y, e4.z, e4.w }, bv4[4] = { b4.x, b4.y, b4.z, b4.w };
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                        {
+                            const float jv = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(al, log_p_step_4), ev[b]), bv4[b]), logz);
+                            s2 = flogsum(s2, jv, tbl);
+                        }
+                        if (s2 > log_p_j1) s2 = log_p_j1;
+                        const float p2 = __fsub_rn(nc_expf(log_p_j1), nc_expf(s2));
+                        t2 = nc_logf(p2);
+#endif
+                        // the item's slot is free once every fold warp has consumed the item ST_RING before it
+                        const unsigned g = base + written + q;
+#if NC_ST_EXP == 9
+                        if (lane == 0) ST_TICK(2);
+#endif
+                        while (g - min(min(v_cons[0], v_cons[1]), v_cons[2]) >= (unsigned)ST_RING)
+                        {
+                            // (an event with more live items than the ring holds: if it has become the oldest unpublished
+                            // one while waiting here, the passes it has completed must be published for the ring to drain)
+                            if (*v_e_pub == ef)
+                            {
+                                __threadfence_block();
+                                *v_pub = base + written + b0;
+                            }
+                            __nanosleep(500);
+                        }
+#if NC_ST_EXP == 9
+                        if (lane == 0) ST_TICK(3);
+#endif
+                        const unsigned slot = g & (ST_RING - 1);
+                        ss.ring[0][slot] = log_p_j1;
+                        ss.ring[1][slot] = jj;
+                        ss.ring[2][slot] = t2;
+                    }
+                    __syncwarp();
+                    // the oldest unpublished event publishes as it goes
+                    if (lane == 0 && *v_e_pub == ef)
+                    {
+                        __threadfence_block();
+                        *v_pub = base + written + min(b0 + 32u, cnt);
+                    }
+                }
+                written += cnt;
+                __syncwarp();
+            }
+            ST_TICK(2);
+#if NC_ST_EXP == 9
+            n_items_dbg += n_live; ++n_ev_dbg;
+#endif
+            // ---- (4) publication in event order
+            if (lane == 0)
+            {
+                while (*v_e_pub != ef) __nanosleep(100);
+                __threadfence_block();
+                *v_pub = base + n_live;
+                __threadfence_block();
+                if (ef + 1u == n_ev) *v_done = 1u;
+                *v_e_pub = ef + 1u;
+            }
+            __syncwarp();
+            ST_TICK(4);
         }
-        if (pt == 0) ss.cnt[buf] = ST_DONE;
-        __syncthreads();
+#if NC_ST_EXP == 9
+        if (lane == 0 && blockIdx.x == 0)
+            printf("st %u producer %d: events %u items %u | phase1 %lld count-wait %lld terms %lld ring-wait %lld publish-wait %lld cycles\n", st, pw, n_ev_dbg,
+                   n_items_dbg, tk[0], tk[1], tk[2], tk[3], tk[4]);
+#endif
     }
     else
     {
         // ================================================= fold warps: denom, stay, skip
+        // Each consumes its ring 32 items at a time as they are published (no CTA-wide barrier: the producers run ahead
+        // by up to ST_RING items).  How the chain is cut into blocks depends on timing; its value does not (fold32 is
+        // exact for any block).
         float acc = NC_NEG_INF;
-        int buf = 0;
+        unsigned c = 0;   // items consumed
+        const volatile float* Tw = ss.ring[warp];
+#if NC_ST_EXP == 9
+        long long tw = 0, tf = 0, t_prev = clock64(); unsigned steps = 0;
+#endif
         for (;;)
         {
-            __syncthreads();
-            const unsigned n_items = ss.cnt[buf];
-            if (n_items == ST_DONE) break;
-            const float* Tw = ss.term[buf][warp];
-#pragma unroll 1
-            for (unsigned base = 0; base < n_items; base += 32)
+            unsigned avail = 0;
+            if (lane == 0)
             {
-                const float x = (base + lane < n_items) ? Tw[base + lane] : NC_NEG_INF;
-                acc = fold32(acc, x, tbl, lane, ss.lst[warp]);
+                for (;;)
+                {
+                    const unsigned fin = *v_done;   // read before pub: if set, pub is final (both volatile: kept in order)
+                    avail = *v_pub - c;
+                    if (avail >= 32u || fin) break;
+                    __nanosleep(200);
+                }
             }
-            if (lane == 0) ss.acc_snap[warp] = acc;
-            buf ^= 1;
+            avail = __shfl_sync(FULL, avail, 0);
+#if NC_ST_EXP == 9
+            { const long long n_ = clock64(); tw += n_ - t_prev; t_prev = n_; ++steps; }
+#endif
+            if (avail == 0u) break;          // (only when the producers are done)
+            const unsigned nb = avail < 32u ? avail : 32u;
+            const float x = ((unsigned)lane < nb) ? Tw[(c + (unsigned)lane) & (ST_RING - 1)] : NC_NEG_INF;
+#if NC_ST_EXP == 2
+            {
+                float mx = x;
+                for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, d));
+                acc = fmaxf(acc, mx);
+            }
+#else
+            acc = fold32(acc, x, tbl, lane, ss.lst[warp]);
+#endif
+            c += nb;
+            if (lane == 0) { v_cons[warp] = c; v_snap[warp] = acc; }
+#if NC_ST_EXP == 9
+            { const long long n_ = clock64(); tf += n_ - t_prev; t_prev = n_; }
+#endif
         }
+#if NC_ST_EXP == 9
+        if (lane == 0 && blockIdx.x == 0) printf("st %u fold %d: items %u steps %u | wait %lld fold %lld cycles | all CTAs so far: blocks %llu speculative %llu exact rounds %llu fallbacks %llu live items %llu\n", st, warp, c, steps, tw, tf, g_dbg[0], g_dbg[1], g_dbg[2], g_dbg[3], g_dbg[4]);
+#endif
         if (lane == 0) a.st_stats[(grp * 2 + st) * 3 + warp] = acc;   // denom, stay, skip
     }
 }

@@ -99,7 +99,17 @@ struct TblPtr   // any address space, index through a float -> int conversion
         return (unsigned)(int)fmul(dc, 1000.0f);
 #endif
     }
-    NC_HD float load(unsigned a) const { return p[a]; }
+    NC_HD float load(unsigned a) const
+    {
+#ifdef __CUDA_ARCH__
+        // read-only for the lifetime of the kernel; kept in L1 against the streaming loads around it
+        float v;
+        asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p + a));
+        return v;
+#else
+        return p[a];
+#endif
+    }
     NC_HD float operator()(float d) const { return load(addr(d)); }
 };
 #ifdef __CUDACC__

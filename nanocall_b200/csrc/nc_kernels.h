@@ -137,6 +137,8 @@ __global__ void pm_stats_kernel(const FbArgs a);
 __global__ void st_stats_kernel(const FbArgs a);
 size_t fwbw_smem_bytes();
 size_t st_stats_smem_bytes();
+unsigned st_stats_threads();
+unsigned st_stats_max_kmers();
 size_t pm_stats_smem_bytes();
 
 } // namespace nc

@@ -290,7 +290,7 @@ int run_wave(nc_ctx* ctx, const Wave& w, const float* d_mean, const float* d_std
     NC_CUDA(ctx, cudaEventRecord(ctx->evk[3], s));
     if (st_stats && ng)
     {
-        nc::st_stats_kernel<<< dim3(ng, 2), 512, nc::st_stats_smem_bytes(), s >>>(a);
+        nc::st_stats_kernel<<< dim3(ng, 2), nc::st_stats_threads(), nc::st_stats_smem_bytes(), s >>>(a);
         NC_CUDA(ctx, cudaGetLastError());
         ++launches;
     }
@@ -403,8 +403,8 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
         if (ev_off[s + 1] <= ev_off[s]) NC_FAIL(ctx, NC_ERR_ARG, "nc_train_round_batch: sequence %u has no events", s);
         if (seq_strand[s] > 1) NC_FAIL(ctx, NC_ERR_ARG, "nc_train_round_batch: sequence %u: strand must be 0 or 1", s);
     }
-    if (ctx->n_train_kmers > 6u * 416u)   // st_stats_kernel: 6 training k-mers per producer thread (2160 for 6-mers)
-        NC_FAIL(ctx, NC_ERR_STATE, "nc_train_round_batch: %u training k-mers exceed the kernel's 2496", ctx->n_train_kmers);
+    if (ctx->n_train_kmers > nc::st_stats_max_kmers())   // st_stats_kernel: a fixed number of training k-mers per producer thread (2160 for 6-mers)
+        NC_FAIL(ctx, NC_ERR_STATE, "nc_train_round_batch: %u training k-mers exceed the kernel's %u", ctx->n_train_kmers, nc::st_stats_max_kmers());
     const uint64_t base = ev_off[0];
     const size_t total = ev_off[n_seqs] - base;
     std::vector< float > yfix;
