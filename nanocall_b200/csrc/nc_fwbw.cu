@@ -156,6 +156,8 @@ __device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl,
     return acc;
 }
 
+__device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct FbSmem
 {
     float tbl[fb::TBL_N];
@@ -309,6 +311,9 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
             int cur = 0;
             for (unsigned i = 1; i < n; ++i)
             {
+                // the emissions were written for the whole wave before this kernel started (far more than L2 holds): the
+                // next column's row is fetched into L2 now, so that its loads wait for L2 and not for DRAM
+                if (t < 128 && i + 1 < n) prefetch_l2(E + (size_t)(i + 1) * NC_N_STATES + 32 * t);
                 const float* Ei = E + (size_t)i * NC_N_STATES + j0;
                 const float4 e0 = __ldg(reinterpret_cast< const float4* >(Ei));
                 const float4 e1 = __ldg(reinterpret_cast< const float4* >(Ei + 4));
@@ -357,6 +362,7 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
             int cur = 0;
             for (unsigned ip1 = n - 1; ip1 > 0; --ip1)
             {
+                if (t < 128 && ip1 >= 2) prefetch_l2(E + (size_t)(ip1 - 1) * NC_N_STATES + 32 * t);
                 float* Bc = sm.col[cur ^ 1];
                 float* Bo = BE + (size_t)(ip1 - 1) * NC_N_STATES;
                 fb::bwd_column(C, sm.col[cur], E + (size_t)ip1 * NC_N_STATES, sm.lut, tbl,

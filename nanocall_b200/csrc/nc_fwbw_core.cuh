@@ -380,29 +380,47 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-// Thread t owns j = t + 512k, k = 0..7: all eight share the two-step successor block [tb, tb+16), tb = 16(t&255);
-// family f = k & 1 (four states) shares the one-step block [ob_f, ob_f+4), ob_f = 4(t + 512f).
+// Backward ownership.  A family is the four states j = j0 + 1024 q, q = 0..3, with j0 = lo + 256 rho (lo = j & 255,
+// rho = 0..3): they share the two-step successor block [tb, tb+16), tb = 16 lo, and the one-step block [ob, ob+4),
+// ob = 4 j0.  The work of a family (folds per column) depends on where its states lie relative to the two blocks:
+// 31 (lo < 32, rho = 2) to 111 (lo >= 224, rho = 3) for a 32-lane range of lo.  Every thread runs two families, and
+// every warp the 32 lanes of two (lo range, rho) items of complementary cost (BWD_ITEMS: 141..153 folds per warp and
+// column; with the two families of the same lo, as the states t + 512 k would give, it is 80..204, and the column
+// barrier waits for the slowest warp).  The price is that the two families of a thread no longer share their
+// two-step block: four more 16-byte loads from each of the two columns and 32 more additions per thread and column.
+NC_HD void bwd_item(int t, int f, int& lo, int& rho)
+{
+    // warp -> { lo range, rho } of family 0 and of family 1 (tools/fwbw_balance.py)
+    const unsigned char BWD_ITEMS[16][4] = { {0, 2, 7, 3}, {0, 3, 5, 2}, {1, 0, 2, 1}, {1, 1, 0, 0}, {0, 1, 7, 2}, {2, 2, 6, 1},
+                                             {1, 2, 6, 0}, {2, 3, 7, 1}, {1, 3, 7, 0}, {3, 0, 5, 3}, {3, 1, 4, 1}, {4, 2, 6, 3},
+                                             {2, 0, 6, 2}, {3, 2, 4, 0}, {4, 3, 5, 1}, {3, 3, 5, 0} };
+    const int w = t >> 5;
+    lo = 32 * (int)BWD_ITEMS[w][2 * f] + (t & 31);
+    rho = (int)BWD_ITEMS[w][2 * f + 1];
+}
 struct BwdConst
 {
-    int t;
-    int tb;          // first two-step successor
+    int j0[2];       // first state of family f (the others: + 1024 q)
+    int tb[2];       // first two-step successor of family f
     int ob[2];       // first one-step successor of family f
-    float wTb;       // weight of the two-step edges
-    float wOb[2];    // weight of the one-step edges of family f
-    unsigned smask[2];  // 6-bit self masks of the 8 states: state k at bits 6(k>>1) of smask[k&1]
+    float wTb[2];    // weight of the two-step edges
+    float wOb[2];    // weight of the one-step edges
+    unsigned smask[2];  // 6-bit self masks of the family's states: state q at bits 6 q
     unsigned flags;  // bit f: oIn[f] (one-step block inside the two-step block), bit 2+f: oBef[f] (one-step block first),
                      // bits 4+2f..5+2f: c4[f] = position (0..3) of the one-step block inside the two-step block
-    unsigned paths;  // 3 bits per state (warp-uniform): 0 = generic chain, 1 = self after both blocks,
+    unsigned paths;  // 3 bits per state k = 2 q + f (warp-uniform): 0 = generic chain, 1 = self after both blocks,
                      // 2 = self between the blocks, one-step block first, 3 = self between, two-step block first,
                      // 4 = self before both blocks
 };
 
-// per-lane classification of state k of thread t: the kernel (and the emulation) turn it into `paths` with a vote
+// per-lane classification of state k = 2 q + f of thread t: the kernel (and the emulation) turn it into `paths` with a vote
 NC_HD unsigned bwd_lane_code(int t, int k)
 {
-    const int j = t + THREADS * k;
-    const int f = k & 1;
-    const int tb = (t & 255) << 4, ob = (t + 512 * f) << 2;
+    const int f = k & 1, q = k >> 1;
+    int lo, rho;
+    bwd_item(t, f, lo, rho);
+    const int j0 = lo + 256 * rho, j = j0 + 1024 * q;
+    const int tb = lo << 4, ob = j0 << 2;
     const bool oIn = (ob >> 4) == (tb >> 4);
     const bool oBef = !oIn && ob < tb;
     const bool sInT = (j >> 4) == (tb >> 4), sInO = (j >> 2) == (ob >> 2);
@@ -415,63 +433,65 @@ NC_HD unsigned bwd_lane_code(int t, int k)
 
 NC_HD void bwd_const_init(BwdConst& C, int t, const float* __restrict__ lut)
 {
-    C.t = t;
-    C.tb = (t & 255) << 4;
-    C.wTb = lut[tmask((unsigned)t, (unsigned)C.tb) & 0x3cu];
     unsigned fl = 0;
-    C.smask[0] = C.smask[1] = 0;
     for (int f = 0; f < 2; ++f)
     {
-        C.ob[f] = (t + 512 * f) << 2;
-        C.wOb[f] = lut[tmask((unsigned)(t + 512 * f), (unsigned)C.ob[f]) & 0x3eu];
-        const bool oIn = (C.ob[f] >> 4) == (C.tb >> 4);
-        const bool oBef = !oIn && C.ob[f] < C.tb;
+        int lo, rho;
+        bwd_item(t, f, lo, rho);
+        C.j0[f] = lo + 256 * rho;
+        C.tb[f] = lo << 4;
+        C.ob[f] = C.j0[f] << 2;
+        C.wTb[f] = lut[tmask((unsigned)C.j0[f], (unsigned)C.tb[f]) & 0x3cu];
+        C.wOb[f] = lut[tmask((unsigned)C.j0[f], (unsigned)C.ob[f]) & 0x3eu];
+        const bool oIn = (C.ob[f] >> 4) == (C.tb[f] >> 4);
+        const bool oBef = !oIn && C.ob[f] < C.tb[f];
         if (oIn) fl |= 1u << f;
         if (oBef) fl |= 1u << (2 + f);
         fl |= (unsigned)((C.ob[f] & 15) >> 2) << (4 + 2 * f);
-    }
-    for (int k = 0; k < 8; ++k)
-    {
-        const unsigned j = (unsigned)(t + THREADS * k);
-        C.smask[k & 1] |= tmask(j, j) << (6 * (k >> 1));
+        C.smask[f] = 0;
+        for (int q = 0; q < 4; ++q)
+        {
+            const unsigned j = (unsigned)(C.j0[f] + 1024 * q);
+            C.smask[f] |= tmask(j, j) << (6 * q);
+        }
     }
     C.flags = fl;
     C.paths = 0;   // filled by the caller from bwd_lane_code with a warp vote
 }
 
 // One column: Bn = beta[i+1] (padded layout), En = emissions of column i+1 (plain layout, global memory),
-// lut = the job's 64 transition weights; out[k] = beta[i][t + 512k].
+// lut = the job's 64 transition weights; store(j, beta[i][j]) for the thread's eight states.
 template < typename TB, typename Store >
 NC_HD void bwd_column(const BwdConst& C, const float* __restrict__ Bn, const float* __restrict__ En,
                       const float* __restrict__ lut, const TB& tbl, Store store)
 {
     const float NI = neg_inf();
-    float vT[16];
-    {
-        const float4* e4 = reinterpret_cast< const float4* >(En + C.tb);
-        const float4* b4 = reinterpret_cast< const float4* >(Bn + cphys(C.tb));
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-        for (int v = 0; v < 4; ++v)
-        {
-#ifdef __CUDA_ARCH__
-            const float4 e = __ldg(e4 + v);
-#else
-            const float4 e = e4[v];
-#endif
-            const float4 b = b4[v];
-            vT[4 * v + 0] = fadd(fadd(C.wTb, e.x), b.x);
-            vT[4 * v + 1] = fadd(fadd(C.wTb, e.y), b.y);
-            vT[4 * v + 2] = fadd(fadd(C.wTb, e.z), b.z);
-            vT[4 * v + 3] = fadd(fadd(C.wTb, e.w), b.w);
-        }
-    }
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int f = 0; f < 2; ++f)
     {
+        float vT[16];
+        {
+            const float4* e4 = reinterpret_cast< const float4* >(En + C.tb[f]);
+            const float4* b4 = reinterpret_cast< const float4* >(Bn + cphys(C.tb[f]));
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int v = 0; v < 4; ++v)
+            {
+#ifdef __CUDA_ARCH__
+                const float4 e = __ldg(e4 + v);
+#else
+                const float4 e = e4[v];
+#endif
+                const float4 b = b4[v];
+                vT[4 * v + 0] = fadd(fadd(C.wTb[f], e.x), b.x);
+                vT[4 * v + 1] = fadd(fadd(C.wTb[f], e.y), b.y);
+                vT[4 * v + 2] = fadd(fadd(C.wTb[f], e.z), b.z);
+                vT[4 * v + 3] = fadd(fadd(C.wTb[f], e.w), b.w);
+            }
+        }
         float vO[4];
         {
 #ifdef __CUDA_ARCH__
@@ -531,7 +551,7 @@ NC_HD void bwd_column(const BwdConst& C, const float* __restrict__ Bn, const flo
         for (int kk = 0; kk < 4; ++kk)
         {
             const int k = 2 * kk + f;
-            const int j = C.t + THREADS * k;
+            const int j = C.j0[f] + 1024 * kk;
             const float wS = lut[(C.smask[f] >> (6 * kk)) & 63u];
 #ifdef __CUDA_ARCH__
             const float eS = __ldg(En + j);
@@ -570,11 +590,11 @@ NC_HD void bwd_column(const BwdConst& C, const float* __restrict__ Bn, const flo
             {
                 // generic: self at its place in the list.  mpos = its position when it coincides with a block entry
                 // (it then replaces that entry: one merged edge), else pos = number of blocks entirely below it
-                const bool sInT = (j >> 4) == (C.tb >> 4), sInO = (j >> 2) == (C.ob[f] >> 2);
+                const bool sInT = (j >> 4) == (C.tb[f] >> 4), sInO = (j >> 2) == (C.ob[f] >> 2);
                 int mpos = -1;
                 if (sInT) mpos = (oBef ? 4 : 0) + (j & 15);
                 else if (sInO) mpos = (oBef ? 0 : 16) + (j & 3);
-                const int pos = (mpos >= 0) ? -1 : ((j > C.tb ? 1 : 0) + ((!oIn && j > C.ob[f]) ? 1 : 0));
+                const int pos = (mpos >= 0) ? -1 : ((j > C.tb[f] ? 1 : 0) + ((!oIn && j > C.ob[f]) ? 1 : 0));
                 acc = (pos == 0) ? vS : NI;
                 const float ins4 = (oBef && pos == 1) ? vS : NI, ins16 = (!oBef && pos == 1) ? vS : NI;
 #ifdef __CUDA_ARCH__
