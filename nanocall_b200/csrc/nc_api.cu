@@ -61,6 +61,9 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
     if ((e = cudaFuncSetAttribute(nc::viterbi_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)nc::viterbi_alpha_smem_bytes())) != cudaSuccess)
         return fail("cudaFuncSetAttribute(viterbi_alpha_kernel)", e);
+    if ((e = cudaFuncSetAttribute(nc::viterbi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)nc::viterbi_alpha_smem_bytes())) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(viterbi_cluster_kernel)", e);
     if ((e = cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(stats)", e);
     if ((e = cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset(stats)", e);
     if ((e = cudaMalloc(&ctx->d_abort, sizeof(unsigned))) != cudaSuccess) return fail("cudaMalloc(abort)", e);
@@ -75,6 +78,8 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
     if ((e = cudaHostAlloc(&ctx->h_landed, nc_ctx::LANDED_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess)
         return fail("cudaHostAlloc(landed)", e);
     // streamed event upload (nc_viterbi_packed, host memory): thresholds, overridable for tests
+    if (const char* v = std::getenv("NC_VIT_CLUSTER")) ctx->cluster_on = std::atoi(v) != 0;
+    if (const char* v = std::getenv("NC_VIT_CLUSTER_MIN_EVENTS")) ctx->cluster_min_events = (uint32_t)std::strtoul(v, nullptr, 10);
     if (const char* v = std::getenv("NC_STREAM_IN_MIN_EVENTS")) ctx->stream_in_min_events = std::strtoull(v, nullptr, 10);
     if (const char* v = std::getenv("NC_STREAM_IN_CHUNK")) ctx->stream_in_chunk = std::max< uint64_t >(32, std::strtoull(v, nullptr, 10));
     unsigned hc = std::thread::hardware_concurrency();
@@ -89,7 +94,7 @@ void nc_ctx_destroy(nc_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : { &ctx->jobs, &ctx->order, &ctx->counter, &ctx->path, &ctx->mean, &ctx->stdv, &ctx->start,
-                       &ctx->lstd, &ctx->states, &ctx->moves, &ctx->tb, &ctx->fb_scratch, &ctx->fb_seqs, &ctx->fb_groups, &ctx->fb_jobs,
+                       &ctx->lstd, &ctx->states, &ctx->moves, &ctx->tb, &ctx->cl_col0, &ctx->fb_scratch, &ctx->fb_seqs, &ctx->fb_groups, &ctx->fb_jobs,
                        &ctx->fb_lz, &ctx->fb_pm, &ctx->fb_st, &ctx->fb_counter, &ctx->fb_mean, &ctx->fb_stdv, &ctx->fb_start, &ctx->fb_lstd,
                        &ctx->gen_from_off, &ctx->gen_from_idx, &ctx->gen_from_lp, &ctx->gen_to_off, &ctx->gen_to_idx, &ctx->gen_to_lp,
                        &ctx->gen_bp, &ctx->gen_order, &ctx->gen_counter })
@@ -322,9 +327,25 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     uint32_t n_long = 0;
     while (n_long < n_jobs && jobs[order[n_long]].n_events > alpha_max_len) ++n_long;
     if (n_jobs) max_len = jobs[order[0]].n_events;   // (of the jobs this part handles)
+    // ---- few jobs: a call with at most one job per two SMs would leave SMs idle, and a long read is 0.6 us per event
+    // on one CTA: every job then gets a cluster of two CTAs (viterbi_cluster_kernel) and a fixed extent of the pool
+    bool use_cluster = false;
+    std::vector< unsigned > cl_col0;
+    if (want_path && ctx->cluster_on && ctx->vit_mode != NC_VIT_BACKPOINTER && order_g.empty() && n_jobs > 0
+        && 2 * (size_t)n_jobs <= n_sms && jobs[order[n_jobs - 1]].n_events >= ctx->cluster_min_events)
+    {
+        size_t cols = 0;
+        for (uint32_t k = 0; k < n_jobs; ++k)
+        {
+            cl_col0.push_back((unsigned)cols);
+            cols += jobs[order[k]].n_events;
+        }
+        use_cluster = cols * a_col <= ctx->bp_bytes && cols < 0xffffffffull;
+    }
     unsigned grid_b = 0, fwd_a = 0, tb_a = 0;
     size_t slab_b = 0, slab_a = 0, pool_b = 0;
-    for (;;)
+    if (use_cluster) n_long = 0;
+    for (; !use_cluster;)
     {
         const uint32_t n_short = n_jobs - n_long;
         grid_b = fwd_a = tb_a = 0;
@@ -365,7 +386,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         }
         break;
     }
-    const uint32_t n_short = n_jobs - n_long;
+    const uint32_t n_short = use_cluster ? 0u : n_jobs - n_long;
 
     // ---- dispatch order of the alpha class (nc_plan_dispatch_order, nc_host.cpp): longest-first whenever the pool
     // allows, shorter jobs while the long reads pin most of it
@@ -397,6 +418,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         if (want_path && (rc = dev_reserve(ctx, ctx->gen_bp, (size_t)grid_g * slab_g)) != NC_OK) return rc;
     }
     if ((rc = dev_reserve(ctx, ctx->counter, 2 * sizeof(unsigned))) != NC_OK) return rc;
+    if (use_cluster && (rc = dev_reserve(ctx, ctx->cl_col0, n_jobs * sizeof(unsigned))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->path, n_jobs_all * sizeof(float))) != NC_OK) return rc;
     // alpha kernel control block: tickets | tail, head | release counter of every forward CTA | column allocator.
     // Every allocation of the call happens before its first asynchronous operation (a cudaFree inside dev_reserve is a
@@ -418,7 +440,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         // Big batches in PINNED memory: the kernels start at once and the event arrays follow on a third stream in
         // chunks.  From pageable memory cudaMemcpyAsync is staged and blocks the host, so nothing would overlap
         // (and the chunking would only add small copies): such calls take the plain copy path.
-        stream_in = total >= ctx->stream_in_min_events && order_g.empty();   // (the list-walking kernel does not poll the landed counter)
+        stream_in = total >= ctx->stream_in_min_events && order_g.empty() && !use_cluster;   // (the list-walking and the cluster kernel do not poll the landed counter)
         if (stream_in)
         {
             cudaPointerAttributes at;
@@ -460,6 +482,7 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
     a.tickets = nullptr;
     a.tb_tail = a.tb_head = a.slab_free = nullptr;
     a.colalloc = nullptr;
+    a.job_col0 = nullptr;
     a.stats = ctx->d_stats;
     a.abort_word = ctx->d_abort;
     a.wait_limit = (long long)(ctx->wait_limit_s * 1e9);   // nanoseconds of back-off
@@ -550,6 +573,16 @@ int nc_viterbi_packed(nc_ctx* ctx, uint32_t n_jobs, const uint64_t* ev_off,
         NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->gen_order.p, order_g.data(), order_g.size() * sizeof(unsigned), cudaMemcpyHostToDevice, s));
         NC_CUDA_INFLIGHT(cudaMemsetAsync(ctx->gen_counter.p, 0, sizeof(unsigned), s));
         nc::viterbi_generic_kernel<<< grid_g, 512, nc::viterbi_generic_smem_bytes(), s >>>(gkn, gt);
+        NC_CUDA_INFLIGHT(cudaGetLastError());
+        ++ctx->last_launches;
+    }
+    if (use_cluster)
+    {
+        nc::VitArgs c = a;
+        c.n_jobs = n_jobs;
+        c.job_col0 = (const unsigned*)ctx->cl_col0.p;
+        NC_CUDA_INFLIGHT(cudaMemcpyAsync(ctx->cl_col0.p, cl_col0.data(), n_jobs * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+        nc::viterbi_cluster_kernel<<< 2 * n_jobs, nc::VIT_THREADS / 2, nc::viterbi_alpha_smem_bytes(), s >>>(c);
         NC_CUDA_INFLIGHT(cudaGetLastError());
         ++ctx->last_launches;
     }

@@ -40,7 +40,10 @@ struct nc_ctx
     float* d_logsum_tbl = nullptr;
     std::string err;
     // grow-only scratch
-    DevBuf jobs, order, counter, path, mean, stdv, start, lstd, states, moves, tb;
+    DevBuf jobs, order, counter, path, mean, stdv, start, lstd, states, moves, tb, cl_col0;
+    uint32_t cluster_min_events = 2000;   // calls with at most n_sms/2 jobs, each at least this long, give every job a CTA pair
+    bool cluster_on = false;              // NC_VIT_CLUSTER=1 switches the cluster kernel on: measured slower than one CTA per
+                                          // job (55 ms against 37 ms for a 60 k-event read), see nc_viterbi_alpha.cu
     DevBuf fb_scratch, fb_seqs, fb_groups, fb_jobs, fb_lz, fb_pm, fb_st, fb_counter, fb_mean, fb_stdv, fb_start, fb_lstd;
     // custom default transition table (nc_ctx_set_default_transitions): in force for jobs / strands whose transition
     // parameters equal gen_default

@@ -49,6 +49,7 @@ struct VitArgs
     unsigned* tb_head;          // tickets claimed
     unsigned* slab_free;        // per forward CTA: number of its jobs the traceback service has released
     void* colalloc;             // device-wide allocator of alpha columns (ColAlloc in nc_viterbi_alpha.cu)
+    const unsigned* job_col0;   // viterbi_cluster_kernel: first pool column of job order[q]
     unsigned* abort_word;       // zeroed before the launch; a CTA that waited longer than the deadline for columns or for a
                                 // ticket (the persistent grid is not making progress), or that found the allocator's
                                 // extent list full, writes a non-zero code here and every waiting loop gives up on seeing it:
@@ -64,6 +65,7 @@ struct VitArgs
 __global__ void viterbi_kernel(const VitArgs a);        // backpointer form (long reads: 4 KiB/event of scratch)
 size_t viterbi_smem_bytes();
 __global__ void viterbi_alpha_kernel(const VitArgs a);  // alpha-column form (fast path: 16 KiB/event of scratch)
+__global__ void viterbi_cluster_kernel(const VitArgs a);   // two CTAs (256 threads each, cluster of 2) per job, grid = 2 n_jobs
 size_t viterbi_alpha_smem_bytes();
 size_t viterbi_alpha_colalloc_bytes();
 unsigned viterbi_alpha_max_forward_ctas();   // bound of the allocator's extent list

@@ -269,6 +269,47 @@ def test_many_short_jobs_with_a_full_pool(models, vit_mode, monkeypatch):
             c.close()
 
 
+def test_few_long_jobs_take_the_cluster_kernel(port, models, vit_mode, monkeypatch):
+    """NC_VIT_CLUSTER=1, at most one job per two SMs, each of at least 2000 events: every job is decoded by a cluster of
+    two CTAs (half of the states each, class candidates exchanged through distributed shared memory).  Same bits as
+    the oracle and as the one-CTA-per-job kernel, odd and even lengths, one job and several.  (The kernel is off by
+    default: it is slower than one CTA per job, see nc_viterbi_alpha.cu; the latency of both is printed.)"""
+    if vit_mode != "alpha":
+        pytest.skip("runs once")
+    import time
+    table = models[R73T]["table"]
+    for lengths in ([2500, 7001, 3000, 2048, 12345], [4097], [2000] * 74):
+        batch = synth.make_batch(91 + len(lengths), table, lengths)
+        res = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("NC_VIT_CLUSTER", flag)
+            c = api.Context(0, bp_pool_bytes=4 << 30)
+            try:
+                mid = c.register_model(table, 0)
+                if flag == "1" and len(lengths) < 10:
+                    _check_batch(c, port, table, mid, batch, None, None)
+                res[flag] = c.viterbi(batch["ev_off"], batch["mean"], batch["stdv"], batch["start"], mid)
+                assert c.last_launches() == 1
+            finally:
+                c.close()
+        assert np.array_equal(_bits(res["1"]["path_logprob"]), _bits(res["0"]["path_logprob"]))
+        assert np.array_equal(res["1"]["states"], res["0"]["states"]) and np.array_equal(res["1"]["moves"], res["0"]["moves"])
+    # one read of 60k events: latency with and without the split (printed; the assertion is only on the results)
+    batch = synth.make_batch(97, table, [60000])
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NC_VIT_CLUSTER", flag)
+        c = api.Context(0, bp_pool_bytes=4 << 30)
+        try:
+            mid = c.register_model(table, 0)
+            c.viterbi(batch["ev_off"], batch["mean"], batch["stdv"], batch["start"], mid)
+            out[flag] = c.viterbi(batch["ev_off"], batch["mean"], batch["stdv"], batch["start"], mid)
+            print(f"60k-event read, NC_VIT_CLUSTER={flag}: kernel {c.last_kernel_ms():.2f} ms")
+        finally:
+            c.close()
+    assert np.array_equal(out["1"]["states"], out["0"]["states"])
+
+
 def test_streamed_event_upload(port, models, vit_mode, monkeypatch):
     """Host-memory calls above a size threshold start the kernels first and stream the events behind them in chunks
     (jobs wait for their events to land).  Forced here on a small batch with 4096-event chunks: same bits."""
