@@ -88,8 +88,10 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
     return NC_OK;
 }
 
+void nc_train_timing_report();
 void nc_ctx_destroy(nc_ctx* ctx)
 {
+    nc_train_timing_report();
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);

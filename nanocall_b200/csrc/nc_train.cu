@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstring>
 #include <thread>
 
@@ -343,6 +344,16 @@ int upload_events(nc_ctx* ctx, size_t total, const float* mean, const float* std
 
 extern "C" {
 
+// NC_TRAIN_TIMING=1: where the host time of nc_train_round_batch goes (printed when the context is destroyed)
+double g_train_t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+void nc_train_timing_report()
+{
+    if (!std::getenv("NC_TRAIN_TIMING")) return;
+    std::fprintf(stderr, "nc_train_round_batch host time: validate+upload %.3f s, wave build %.3f, fill_job %.3f, run_wave (launch+kernels+copies) %.3f, finish %.3f, calls %.0f\n",
+                 g_train_t[0], g_train_t[1], g_train_t[2], g_train_t[3], g_train_t[4], g_train_t[5]);
+}
+
+
 int nc_fwbw(nc_ctx* ctx, int32_t model_id, const nc_pm_params* pm, const nc_st_params* st,
             uint32_t n_events, const float* mean, const float* stdv, const float* start,
             float* alpha, float* beta, float* log_pr_data)
@@ -405,11 +416,20 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
     }
     if (ctx->n_train_kmers > nc::st_stats_max_kmers())   // st_stats_kernel: a fixed number of training k-mers per producer thread (2160 for 6-mers)
         NC_FAIL(ctx, NC_ERR_STATE, "nc_train_round_batch: %u training k-mers exceed the kernel's %u", ctx->n_train_kmers, nc::st_stats_max_kmers());
+    const auto tt0 = std::chrono::steady_clock::now();
+    auto lap = [&](int k, std::chrono::steady_clock::time_point& from) {
+        const auto now = std::chrono::steady_clock::now();
+        g_train_t[k] += std::chrono::duration< double >(now - from).count();
+        from = now;
+    };
+    auto tl = tt0;
+    g_train_t[5] += 1;
     const uint64_t base = ev_off[0];
     const size_t total = ev_off[n_seqs] - base;
     std::vector< float > yfix;
     if ((rc = upload_events(ctx, total, mean + base, stdv + base, start + base, yfix)) != NC_OK) return rc;
     const size_t limit_floats = scratch_limit(ctx) / sizeof(float);
+    lap(0, tl);
 
     uint32_t g0 = 0;
     std::vector< float > lz, pm_rows, st_acc;
@@ -455,14 +475,17 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
             w.groups.push_back(G);
             ++g1;
         }
+        lap(1, tl);
         parallel_for(g1 - g0, ctx->host_threads, [&](size_t k) {
             for (int st = 0; st < 2; ++st) fill_job(w.jobs[2 * k + st], in[g0 + k].model_id[st], in[g0 + k].pm, in[g0 + k].st[st]);
         });
+        lap(2, tl);
         if ((rc = run_wave(ctx, w, (const float*)ctx->fb_mean.p, (const float*)ctx->fb_stdv.p, (const float*)ctx->fb_start.p,
                            nullptr, opts->train_scaling != 0, opts->train_transitions != 0,
                            lz, pm_rows, st_acc)) != NC_OK)
             return rc;
         kernel_ms += ctx->last_kernel_ms;
+        lap(3, tl);
         // ---- finish every group of the wave on the host (train_one_round, :541-579)
         parallel_for(g1 - g0, ctx->host_threads, [&](size_t gk)
         {
@@ -494,6 +517,7 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
                 o.st[1] = finish_st(st_acc.data() + (size_t)(g - g0) * 6 + 3);
             }
         });
+        lap(4, tl);
         g0 = g1;
     }
     ctx->last_kernel_ms = kernel_ms;
