@@ -172,6 +172,11 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
 int nc_ctx_set_default_transitions(nc_ctx* ctx, float p_stay_default, float p_skip_default, uint32_t n_edges,
                                    const uint16_t* from, const uint16_t* to, const float* logp);
 
+/* Optional: allocate now what calls of this size will need (Forward/Backward scratch for train_events events per call, up
+ * to the context's limit; device staging for NC_MEM_HOST Viterbi calls of viterbi_events events), so that the first
+ * call does not pay for it.  No reference counterpart (the reference allocates per read, Forward_Backward.hpp:52-56). */
+int nc_ctx_reserve(nc_ctx* ctx, uint64_t train_events, uint64_t viterbi_events);
+
 /* Page-locked host memory for the event / state / move arrays of NC_MEM_HOST calls.  Optional: any host memory works,
  * but only pinned buffers are copied at full PCIe rate and let nc_viterbi_packed stream the events behind the kernel
  * launch.  nc_host_alloc returns NULL when the allocation fails (or there is no CUDA device). */

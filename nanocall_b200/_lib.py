@@ -67,6 +67,7 @@ SYMBOLS = {
     "nc_train_round_batch": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nc_ctx_train_stats": (C.c_int, [_vp, _vp, C.c_int]),
     "nc_ctx_set_default_transitions": (C.c_int, [_vp, _f, _f, _u32, _vp, _vp, _vp]),
+    "nc_ctx_reserve": (C.c_int, [_vp, C.c_uint64, C.c_uint64]),
     "nc_host_alloc": (_vp, [C.c_size_t]),
     "nc_host_free": (None, [_vp]),
     "nc_mean_stdv": (None, [_u32, _vp, C.POINTER(_f), C.POINTER(_f)]),

@@ -53,6 +53,7 @@ struct nc_ctx
     unsigned* d_train_kmers = nullptr;
     unsigned n_train_kmers = 0;
     size_t fb_scratch_limit = 0;  // bytes of E|alpha|beta slabs per wave (0 = pick from free memory)
+    size_t fb_scratch_auto = 0;    // the limit derived from the free memory, once
     unsigned host_threads = 1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evk[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // around the four training kernels of a wave

@@ -95,10 +95,14 @@ void fill_job(nc::DevJob& J, int model, const nc_pm_params& pm, const nc_st_para
 size_t scratch_limit(nc_ctx* ctx)
 {
     if (ctx->fb_scratch_limit) return ctx->fb_scratch_limit;
+    // (asked once per context: cudaMemGetInfo takes ~13 ms on a 180 GB device with a large pool allocated, which was a
+    // quarter of a second over the 20 EM rounds of a batch)
+    if (ctx->fb_scratch_auto) return ctx->fb_scratch_auto;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (size_t)1 << 30;
     size_t have = ctx->fb_scratch.cap;
-    return std::min< size_t >((free_b + have) / 2, (size_t)24 << 30);
+    ctx->fb_scratch_auto = std::min< size_t >((free_b + have) / 2, (size_t)24 << 30);
+    return ctx->fb_scratch_auto;
 }
 
 // train_pm_params after the inner sums (Parameter_Trainer.hpp:297-427).  rows: per event {s0,s1,s2,l0,l1,l2};
@@ -349,8 +353,8 @@ double g_train_t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 void nc_train_timing_report()
 {
     if (!std::getenv("NC_TRAIN_TIMING")) return;
-    std::fprintf(stderr, "nc_train_round_batch host time: validate+upload %.3f s, wave build %.3f, fill_job %.3f, run_wave (launch+kernels+copies) %.3f, finish %.3f, calls %.0f\n",
-                 g_train_t[0], g_train_t[1], g_train_t[2], g_train_t[3], g_train_t[4], g_train_t[5]);
+    std::fprintf(stderr, "nc_train_round_batch host time: upload %.3f s, scratch_limit %.3f, wave build %.3f, fill_job %.3f, run_wave (launch+kernels+copies) %.3f, finish %.3f, calls %.0f\n",
+                 g_train_t[6], g_train_t[7], g_train_t[1], g_train_t[2], g_train_t[3], g_train_t[4], g_train_t[5]);
 }
 
 
@@ -428,8 +432,9 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
     const size_t total = ev_off[n_seqs] - base;
     std::vector< float > yfix;
     if ((rc = upload_events(ctx, total, mean + base, stdv + base, start + base, yfix)) != NC_OK) return rc;
+    lap(6, tl);
     const size_t limit_floats = scratch_limit(ctx) / sizeof(float);
-    lap(0, tl);
+    lap(7, tl);
 
     uint32_t g0 = 0;
     std::vector< float > lz, pm_rows, st_acc;
@@ -521,6 +526,30 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
         g0 = g1;
     }
     ctx->last_kernel_ms = kernel_ms;
+    return NC_OK;
+}
+
+int nc_ctx_reserve(nc_ctx* ctx, uint64_t train_events, uint64_t viterbi_events)
+{
+    if (!ctx) return NC_ERR_ARG;
+    NC_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (train_events)
+    {
+        if ((rc = ensure_train_tables(ctx)) != NC_OK) return rc;
+        const size_t want = std::min< size_t >(scratch_limit(ctx), (size_t)train_events * 3 * NC_N_STATES * sizeof(float));
+        if ((rc = dev_reserve(ctx, ctx->fb_scratch, want)) != NC_OK) return rc;
+        if ((rc = dev_reserve(ctx, ctx->fb_pm, (size_t)train_events * 6 * sizeof(float))) != NC_OK) return rc;
+        for (DevBuf* b : { &ctx->fb_mean, &ctx->fb_stdv, &ctx->fb_start })
+            if ((rc = dev_reserve(ctx, *b, (size_t)train_events * sizeof(float))) != NC_OK) return rc;
+    }
+    if (viterbi_events)
+    {
+        for (DevBuf* b : { &ctx->mean, &ctx->stdv, &ctx->start })
+            if ((rc = dev_reserve(ctx, *b, (size_t)viterbi_events * sizeof(float))) != NC_OK) return rc;
+        if ((rc = dev_reserve(ctx, ctx->states, (size_t)viterbi_events * sizeof(uint16_t))) != NC_OK) return rc;
+        if ((rc = dev_reserve(ctx, ctx->moves, (size_t)viterbi_events)) != NC_OK) return rc;
+    }
     return NC_OK;
 }
 

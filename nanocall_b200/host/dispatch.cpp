@@ -214,6 +214,8 @@ bool run_pipeline(const Run_Config& cfg, Read_Source& src, std::ostream* fasta, 
                         p.reset(new Pipeline(cfg.opt, cfg.devices[g], hint));
                         p->init_models();
                         p->init_transitions();
+                        // one-time allocations for batches like this one (later, larger batches grow them as needed)
+                        p->reserve(batch.size(), ev);
                         ds.init_s = secs(i0, Clock::now());
                     }
                     if (!first_batch_seen.exchange(true))

@@ -172,6 +172,23 @@ void Pipeline::init_models()
 
 // init_transitions (nanocall.cpp:180-193): a custom initial table (-s/--trans, State_Transitions::operator>>,
 // State_Transitions.hpp:237-252: lines "kmer_i kmer_j log_prob", kept in file order), or the parametric one
+void Pipeline::reserve(size_t reads, size_t events)
+{
+    // training: two candidate pairs per read x two strands x scaling_num_events events, at most
+    const size_t train_events = opt_.train ? reads * 2 * 2 * (size_t)opt_.scaling_num_events : 0;
+    // basecalling: every strand once per candidate still in the race (two at most with the builtin presets)
+    const size_t vit_events = opt_.basecall ? 2 * events : 0;
+    check(nc_ctx_reserve(ctx_, train_events, vit_events), "nc_ctx_reserve");
+    if (vit_events)
+    {
+        pin_mean_.reserve(vit_events * sizeof(float));
+        pin_stdv_.reserve(vit_events * sizeof(float));
+        pin_start_.reserve(vit_events * sizeof(float));
+        pin_states_.reserve(vit_events * sizeof(uint16_t));
+        pin_moves_.reserve(vit_events);
+    }
+}
+
 void Pipeline::init_transitions()
 {
     if (opt_.trans_fn.empty())

@@ -103,6 +103,9 @@ public:
 
     void init_models();
     void init_transitions();
+    // allocate now what batches of up to `reads` reads / `events` events will need (device scratch, pinned staging), so
+    // that the first batch does not pay for it
+    void reserve(size_t reads, size_t events);
     void init_read_params(Read& r) const;
     void train_reads(std::vector< Read* >& reads);
     void basecall_reads(std::vector< Read* >& reads);
