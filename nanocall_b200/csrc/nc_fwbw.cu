@@ -77,6 +77,9 @@ __device__ __forceinline__ float fold_logsum_in_order(float acc, const int n, Ge
 #ifndef NC_ST_EXP
 #define NC_ST_EXP 0   // timing experiments only: 1 = no phase-2 arithmetic, 2 = no fold; anything but 0 is not a product build
 #endif
+#ifndef NC_ST_BLOCK
+#define NC_ST_BLOCK 32   // 64: fold64 when that many terms are published (measured: a chain alone 2.60 -> 2.45 ms, but a full wave 19.9 -> 21.3 ms: more instructions per term)
+#endif
 #ifndef NC_ST_PRE
 #define NC_ST_PRE 1
 #endif
@@ -156,6 +159,85 @@ __device__ __forceinline__ float fold32(float acc, const float x, const TB& tbl,
     return acc;
 }
 
+// The same step for 64 terms (lane l holds terms l and 32 + l).  Most of a step's time is fixed -- two table lookups that
+// wait for the slowest lane, the votes, the list -- so twice the terms per step is what makes the chain faster; the
+// per-term work (one FADD on the chain, the captures off it) is the same.  lst: 72 floats.
+template < typename TB >
+__device__ __forceinline__ float fold64(float acc, const float x0, const float x1, const TB& tbl, const int lane, float* __restrict__ lst)
+{
+    const bool live0 = !((x0 == NC_NEG_INF) || (acc > x0 && __fsub_rn(acc, x0) >= 15.999f));
+    const bool live1 = !((x1 == NC_NEG_INF) || (acc > x1 && __fsub_rn(acc, x1) >= 15.999f));
+    const unsigned m0 = __ballot_sync(FULL, live0), m1 = __ballot_sync(FULL, live1);
+    if ((m0 | m1) == 0u) return acc;
+    const bool spec_ok = __all_sync(FULL, (!live0 || acc >= x0) && (!live1 || acc >= x1));
+    if (spec_ok)
+    {
+        const float INF = __int_as_float(0x7f800000);
+        const unsigned lt = (1u << lane) - 1u;
+        const int L0 = __popc(m0), L = L0 + __popc(m1);
+        const int r0 = __popc(m0 & lt), r1 = L0 + __popc(m1 & lt);   // live terms before each of this lane's two
+        unsigned e0 = tbl.addr(live0 ? __fsub_rn(acc, x0) : INF), e1 = tbl.addr(live1 ? __fsub_rn(acc, x1) : INF);
+#pragma unroll
+        for (int pre = 0; pre < NC_ST_PRE; ++pre)
+        {
+            float p0 = live0 ? tbl.load(e0) : 0.0f, p1 = live1 ? tbl.load(e1) : 0.0f;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const float v0 = __shfl_up_sync(FULL, p0, d), v1 = __shfl_up_sync(FULL, p1, d);
+                if (lane >= d) { p0 = __fadd_rn(p0, v0); p1 = __fadd_rn(p1, v1); }
+            }
+            const float tot0 = __shfl_sync(FULL, p0, 31);
+            const float b0 = __shfl_up_sync(FULL, p0, 1), b1 = __shfl_up_sync(FULL, p1, 1);
+            const float est0 = __fadd_rn(acc, lane ? b0 : 0.0f);
+            const float est1 = __fadd_rn(acc, __fadd_rn(tot0, lane ? b1 : 0.0f));
+            e0 = tbl.addr(live0 ? fmaxf(__fsub_rn(est0, x0), 0.0f) : INF);
+            e1 = tbl.addr(live1 ? fmaxf(__fsub_rn(est1, x1), 0.0f) : INF);
+        }
+#pragma unroll 1
+        for (int round = 0; round < 3; ++round)
+        {
+            const float t0 = tbl.load(e0), t1 = tbl.load(e1);
+            if (live0) lst[r0] = t0;
+            if (live1) lst[r1] = t1;
+            if (lane < 8) lst[L + lane] = 0.0f;
+            __syncwarp();
+            // one chain over all live increments; the lane keeps the running value at its two positions
+            float a = acc, a0 = acc, a1 = acc;
+            float4 v = *reinterpret_cast< const float4* >(lst);
+            for (int k = 0; k < L; k += 4)
+            {
+                const float4 vn = *reinterpret_cast< const float4* >(lst + k + 4);
+                a0 = (k + 0 == r0) ? a : a0; a1 = (k + 0 == r1) ? a : a1; a = __fadd_rn(a, v.x);
+                a0 = (k + 1 == r0) ? a : a0; a1 = (k + 1 == r1) ? a : a1; a = __fadd_rn(a, v.y);
+                a0 = (k + 2 == r0) ? a : a0; a1 = (k + 2 == r1) ? a : a1; a = __fadd_rn(a, v.z);
+                a0 = (k + 3 == r0) ? a : a0; a1 = (k + 3 == r1) ? a : a1; a = __fadd_rn(a, v.w);
+                v = vn;
+            }
+            __syncwarp();
+            const unsigned f0 = tbl.addr(live0 ? __fsub_rn(a0, x0) : INF), f1 = tbl.addr(live1 ? __fsub_rn(a1, x1) : INF);
+            const bool ok = (!live0 || (a0 >= x0 && f0 == e0)) && (!live1 || (a1 >= x1 && f1 == e1));
+            if (__all_sync(FULL, ok))
+            {
+                // the value after the last live increment: a holds acc + all L increments (the padding adds zeros)
+                return __shfl_sync(FULL, a, 0);
+            }
+            e0 = f0; e1 = f1;
+        }
+    }
+    for (unsigned mm = m0; mm; mm &= mm - 1)
+    {
+        const int k = __ffs(mm) - 1;
+        acc = flogsum(acc, __shfl_sync(FULL, x0, k), tbl);
+    }
+    for (unsigned mm = m1; mm; mm &= mm - 1)
+    {
+        const int k = __ffs(mm) - 1;
+        acc = flogsum(acc, __shfl_sync(FULL, x1, k), tbl);
+    }
+    return acc;
+}
+
 __device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct FbSmem
@@ -189,7 +271,7 @@ struct StSmem
     unsigned done;                // set after the last publication
     unsigned cons[4];             // items consumed by each fold warp
     float acc_snap[4];            // running values the fold warps published last
-    __align__(16) float lst[3][40];   // fold32's warp-private lists
+    __align__(16) float lst[3][80];   // fold32's / fold64's warp-private lists
     unsigned seq_id[NC_MAX_TRAIN_SEQS];      // the strand's sequences with >= 2 events, in order
     unsigned seq_first[NC_MAX_TRAIN_SEQS + 1];  // first flattened (event) index of each
     unsigned n_seq;
@@ -778,17 +860,27 @@ __global__ void __launch_bounds__(ST_THREADS, ST_CTAS) st_stats_kernel(const FbA
             { const long long n_ = clock64(); tw += n_ - t_prev; t_prev = n_; ++steps; }
 #endif
             if (avail == 0u) break;          // (only when the producers are done)
-            const unsigned nb = avail < 32u ? avail : 32u;
-            const float x = ((unsigned)lane < nb) ? Tw[(c + (unsigned)lane) & (ST_RING - 1)] : NC_NEG_INF;
-#if NC_ST_EXP == 2
+            unsigned nb;
+#if NC_ST_BLOCK == 64
+            if (avail >= 64u)
             {
+                nb = 64u;
+                const float x0 = Tw[(c + (unsigned)lane) & (ST_RING - 1)], x1 = Tw[(c + 32u + (unsigned)lane) & (ST_RING - 1)];
+                acc = fold64(acc, x0, x1, tbl, lane, ss.lst[warp]);
+            }
+            else
+#endif
+            {
+                nb = avail < 32u ? avail : 32u;
+                const float x = ((unsigned)lane < nb) ? Tw[(c + (unsigned)lane) & (ST_RING - 1)] : NC_NEG_INF;
+#if NC_ST_EXP == 2
                 float mx = x;
                 for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, d));
                 acc = fmaxf(acc, mx);
-            }
 #else
-            acc = fold32(acc, x, tbl, lane, ss.lst[warp]);
+                acc = fold32(acc, x, tbl, lane, ss.lst[warp]);
 #endif
+            }
             c += nb;
             if (lane == 0) { v_cons[warp] = c; v_snap[warp] = acc; }
 #if NC_ST_EXP == 9
