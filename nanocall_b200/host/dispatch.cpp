@@ -132,6 +132,41 @@ private:
     Clock::time_point last_write_ = Clock::now();
 };
 
+// one trained batch on its way from a dispatcher's training thread to its basecalling thread
+class Hand_Over
+{
+public:
+    bool give(std::vector< Item >&& b)   // false: the other side failed
+    {
+        std::unique_lock< std::mutex > lk(mu_);
+        cv_.wait(lk, [&] { return !full_ || failed_; });
+        if (failed_) return false;
+        slot_ = std::move(b);
+        full_ = true;
+        cv_.notify_all();
+        return true;
+    }
+    bool take(std::vector< Item >& b)    // false: nothing will come any more
+    {
+        std::unique_lock< std::mutex > lk(mu_);
+        cv_.wait(lk, [&] { return full_ || closed_ || failed_; });
+        if (!full_) return false;
+        b = std::move(slot_);
+        slot_.clear();
+        full_ = false;
+        cv_.notify_all();
+        return true;
+    }
+    void close() { std::lock_guard< std::mutex > lk(mu_); closed_ = true; cv_.notify_all(); }
+    void fail() { std::lock_guard< std::mutex > lk(mu_); failed_ = true; cv_.notify_all(); }
+
+private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector< Item > slot_;
+    bool full_ = false, closed_ = false, failed_ = false;
+};
+
 } // namespace
 
 bool run_pipeline(const Run_Config& cfg, Read_Source& src, std::ostream* fasta, std::ostream* stats_tsv, Run_Stats& stats)
@@ -186,9 +221,34 @@ bool run_pipeline(const Run_Config& cfg, Read_Source& src, std::ostream* fasta, 
         workers.emplace_back([&, g] {
             Device_Stats& ds = stats.dev[g];
             ds.device = cfg.devices[g];
+            std::unique_ptr< Pipeline > p;
+            // Two threads per GPU share the context: this one trains batch k+1 while the caller thread basecalls batch k
+            // (Pipeline serialises the calls into the context; what overlaps is one thread's host passes -- packing, base
+            // sequences, FASTA -- with the other's kernels).  At most one trained batch waits between them.
+            Hand_Over hand;
+            std::thread caller;
+            auto finish = [&](std::vector< Item >& batch) {
+                std::vector< Read* > rp;
+                size_t ev = 0;
+                for (auto& it : batch)
+                {
+                    rp.push_back(&it.read);
+                    ev += it.events();
+                }
+                const auto a1 = Clock::now();
+                if (cfg.opt.basecall) p->basecall_reads(rp);
+                ds.basecall_s += secs(a1, Clock::now());
+                ds.reads += batch.size();
+                ds.read_events += ev;
+                ++ds.batches;
+                for (auto& it : batch)   // the events are not needed any more
+                    for (unsigned st = 0; st < 2; ++st) it.read.events[st] = Strand_Events();
+                sink.put(std::move(batch));
+                ds.last_batch_done_s = secs(t_start, Clock::now());
+            };
             try
             {
-                std::unique_ptr< Pipeline > p;
+                size_t n_batches = 0;
                 for (;;)
                 {
                     const auto w0 = Clock::now();
@@ -196,7 +256,7 @@ bool run_pipeline(const Run_Config& cfg, Read_Source& src, std::ostream* fasta, 
                     const auto w1 = Clock::now();
                     ds.wait_s += secs(w0, w1);
                     if (batch.empty()) break;
-                    if (ds.batches == 0) ds.first_batch_at_s = secs(t_start, w1);
+                    if (n_batches++ == 0) ds.first_batch_at_s = secs(t_start, w1);
                     size_t longest = 0, ev = 0;
                     for (const auto& it : batch)
                         for (unsigned st = 0; st < 2; ++st)
@@ -217,6 +277,19 @@ bool run_pipeline(const Run_Config& cfg, Read_Source& src, std::ostream* fasta, 
                         // one-time allocations for batches like this one (later, larger batches grow them as needed)
                         p->reserve(batch.size(), ev);
                         ds.init_s = secs(i0, Clock::now());
+                        if (cfg.overlap && cfg.opt.train && cfg.opt.basecall)
+                            caller = std::thread([&] {
+                                try
+                                {
+                                    std::vector< Item > b;
+                                    while (hand.take(b)) finish(b);
+                                }
+                                catch (const std::exception& e)
+                                {
+                                    fail(e.what());
+                                    hand.fail();
+                                }
+                            });
                     }
                     if (!first_batch_seen.exchange(true))
                     {
@@ -233,36 +306,35 @@ bool run_pipeline(const Run_Config& cfg, Read_Source& src, std::ostream* fasta, 
                     }
                     const auto a0 = Clock::now();
                     if (cfg.opt.train) p->train_reads(rp);
-                    const auto a1 = Clock::now();
-                    if (cfg.opt.basecall) p->basecall_reads(rp);
-                    const auto a2 = Clock::now();
-                    ds.train_s += secs(a0, a1);
-                    ds.basecall_s += secs(a1, a2);
-                    ds.reads += batch.size();
-                    ds.read_events += ev;
-                    ++ds.batches;
-                    for (auto& it : batch)   // the events are not needed any more
-                        for (unsigned st = 0; st < 2; ++st) it.read.events[st] = Strand_Events();
-                    sink.put(std::move(batch));
-                    ds.last_batch_done_s = secs(t_start, Clock::now());
-                }
-                if (p)
-                {
-                    ds.train_rounds = p->train_rounds;
-                    ds.fwbw_events = p->fwbw_events;
-                    ds.viterbi_events = p->viterbi_events;
-                    ds.train_kernel_ms = p->train_kernel_ms;
-                    ds.viterbi_kernel_ms = p->viterbi_kernel_ms;
-                    ds.train_call_s = p->train_call_s;
-                    ds.viterbi_call_s = p->viterbi_call_s;
-                    double ts[8];
-                    if (nc_ctx_train_stats(p->ctx(), ts, 0) == NC_OK)
+                    ds.train_s += secs(a0, Clock::now());
+                    if (caller.joinable())
                     {
-                        ds.emission_ms = ts[0]; ds.fwbw_ms = ts[1]; ds.pm_stats_ms = ts[2]; ds.st_stats_ms = ts[3];
+                        const auto h0 = Clock::now();
+                        const bool ok = hand.give(std::move(batch));
+                        ds.hand_wait_s += secs(h0, Clock::now());
+                        if (!ok) break;
                     }
+                    else finish(batch);
                 }
             }
             catch (const std::exception& e) { fail(e.what()); }
+            hand.close();
+            if (caller.joinable()) caller.join();
+            if (p)
+            {
+                ds.train_rounds = p->train_rounds;
+                ds.fwbw_events = p->fwbw_events;
+                ds.viterbi_events = p->viterbi_events;
+                ds.train_kernel_ms = p->train_kernel_ms;
+                ds.viterbi_kernel_ms = p->viterbi_kernel_ms;
+                ds.train_call_s = p->train_call_s;
+                ds.viterbi_call_s = p->viterbi_call_s;
+                double ts[8];
+                if (nc_ctx_train_stats(p->ctx(), ts, 0) == NC_OK)
+                {
+                    ds.emission_ms = ts[0]; ds.fwbw_ms = ts[1]; ds.pm_stats_ms = ts[2]; ds.st_stats_ms = ts[3];
+                }
+            }
         });
     for (auto& t : loaders) t.join();
     for (auto& t : workers) t.join();
@@ -294,7 +366,7 @@ std::string stats_json(const Run_Config& cfg, const Run_Stats& s)
            << ", \"viterbi_events\": " << d.viterbi_events << ", \"viterbi_kernel_ms\": " << d.viterbi_kernel_ms
            << ", \"init_s\": " << d.init_s << ", \"train_s\": " << d.train_s << ", \"basecall_s\": " << d.basecall_s
            << ", \"train_call_s\": " << d.train_call_s << ", \"viterbi_call_s\": " << d.viterbi_call_s
-           << ", \"wait_s\": " << d.wait_s << ", \"first_batch_at_s\": " << d.first_batch_at_s
+           << ", \"wait_s\": " << d.wait_s << ", \"hand_wait_s\": " << d.hand_wait_s << ", \"first_batch_at_s\": " << d.first_batch_at_s
            << ", \"last_batch_done_s\": " << d.last_batch_done_s << "}";
     }
     double last = 0, first_done = 1e300;

@@ -30,6 +30,7 @@ struct Cli
     int gpus = 1;
     int first_device = 0;
     size_t batch_reads = 4096, batch_mevents = 48, pool_gb = 0;
+    bool overlap = true;
     unsigned loader_threads = 0;
     bool single_strand_scaling = false, double_strand_flag = false, train_flag = false, no_train = false;
     bool basecall_flag = false, no_basecall = false, write_fast5 = false, summarize_only = false;
@@ -51,7 +52,7 @@ void usage()
         "  --ed-group G   --chunk-size N   --basecall / --no-basecall   --fasta-line-width N (80)\n"
         "  -o/--output file   --stats file   --log [facility:]level (multi)   -t/--threads N (host loader threads)\n"
         "  --write-fast5 (needs HDF5: rejected in this build)   --version   --help\n"
-        "  device options: --gpus N (1)   --device K (0)   --batch-reads N (4096)   --batch-mevents N (48)   --pool-gb N\n"
+        "  device options: --gpus N (1)   --device K (0)   --batch-reads N (4096)   --batch-mevents N (48)   --pool-gb N   --no-overlap\n"
         "  --synth n[:seed[:pool[:2d|1d|mix[:nt[:nc]]]]]   synthetic R7.3 reads instead of inputs\n"
         "  --summary-json file      run statistics (per-GPU device times, events/s, tail)\n"
         "  --summarize-only         segmentation and --stats without a GPU (no training, no basecalling)\n";
@@ -130,6 +131,7 @@ int parse(int argc, char** argv, Cli& c)
         else if (a == "--device") c.first_device = std::atoi(need(i));
         else if (a == "--batch-reads") c.batch_reads = (size_t)std::atoll(need(i));
         else if (a == "--batch-mevents") c.batch_mevents = (size_t)std::atoll(need(i));
+        else if (a == "--no-overlap") c.overlap = false;
         else if (a == "--pool-gb") c.pool_gb = (size_t)std::atoll(need(i));
         else if (a == "--synth") c.synth = need(i);
         else if (a == "--summary-json") c.summary_json = need(i);
@@ -274,6 +276,7 @@ int main(int argc, char** argv)
     for (int g = 0; g < cli.gpus; ++g) cfg.devices.push_back(cli.first_device + g);
     cfg.batch_reads = std::max< size_t >(1, cli.batch_reads);
     cfg.batch_events = std::max< size_t >(1, cli.batch_mevents) << 20;
+    cfg.overlap = cli.overlap;
     cfg.queue_events = std::max(cfg.batch_events * (cfg.devices.size() + 1), (size_t)192 << 20);
     cfg.loader_threads = cli.loader_threads;
     cfg.pool_bytes = cli.pool_gb << 30;

@@ -21,7 +21,7 @@ namespace nchost {
 
 void log_line(int level, int threshold, const std::string& msg)
 {
-    if (level <= threshold) std::clog << msg << std::endl;
+    if (level <= threshold) std::clog << (msg + "\n") << std::flush;   // one insertion per line: several threads log
 }
 
 #define NLOG(lvl, expr)                                   \
@@ -29,7 +29,8 @@ void log_line(int level, int threshold, const std::string& msg)
         if ((lvl) <= opt_.log_level) {                    \
             std::ostringstream _o;                        \
             _o << expr;                                   \
-            std::clog << _o.str() << std::endl;           \
+            _o << '\n';                                   \
+            std::clog << _o.str() << std::flush;          \
         }                                                 \
     } while (0)
 
@@ -417,12 +418,15 @@ void Pipeline::train_reads(std::vector< Read* >& reads)
             tin[a].st[0] = c.crt_st[0];
             tin[a].st[1] = c.crt_st[1];
         }
-        const auto c0 = std::chrono::steady_clock::now();
-        check(nc_train_round_batch(ctx_, (uint32_t)act.size(), seq_off.data(), ev_off.data(), strands.data(),
-                                   mean.data(), stdv.data(), start.data(), tin.data(), &topts, tout.data()),
-              "nc_train_round_batch");
-        train_call_s += std::chrono::duration< double >(std::chrono::steady_clock::now() - c0).count();
-        train_kernel_ms += nc_ctx_last_kernel_ms(ctx_);
+        {
+            std::lock_guard< std::mutex > gpu(gpu_mu_);
+            const auto c0 = std::chrono::steady_clock::now();
+            check(nc_train_round_batch(ctx_, (uint32_t)act.size(), seq_off.data(), ev_off.data(), strands.data(),
+                                       mean.data(), stdv.data(), start.data(), tin.data(), &topts, tout.data()),
+                  "nc_train_round_batch");
+            train_call_s += std::chrono::duration< double >(std::chrono::steady_clock::now() - c0).count();
+            train_kernel_ms += nc_ctx_last_kernel_ms(ctx_);
+        }
         ++train_rounds;
         fwbw_events += ev_off.back();
         for (size_t a = 0; a < act.size(); ++a)
@@ -638,9 +642,10 @@ void Pipeline::basecall_reads(std::vector< Read* >& reads)
             }
         });
         for (const auto& w : warn)
-            if (!w.empty()) std::clog << w << std::endl;
+            if (!w.empty()) std::clog << (w + "\n") << std::flush;
         if (nj)
         {
+            std::lock_guard< std::mutex > gpu(gpu_mu_);
             const auto c0 = std::chrono::steady_clock::now();
             check(nc_viterbi_packed(ctx_, nj, off.data(), mean, stdv, start, nullptr, mid.data(),
                                     pm.data(), st.data(), NC_MEM_HOST, path.data(), states, moves),

@@ -17,6 +17,7 @@
 #include <array>
 #include <iosfwd>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -135,6 +136,9 @@ private:
     Pinned pin_mean_, pin_stdv_, pin_start_, pin_states_, pin_moves_;
     Options opt_;
     nc_ctx* ctx_ = nullptr;
+    // train_reads and basecall_reads may run on two threads (dispatch.cpp trains batch k+1 while batch k is basecalled):
+    // the calls into the context are serialised here, the host passes around them are not
+    std::mutex gpu_mu_;
     std::map< std::string, Model > models_;  // ordered by name, as Pore_Model_Dict (std::map)
 };
 
