@@ -73,6 +73,7 @@ int nc_ctx_create(int device, size_t bp_pool_bytes, nc_ctx** out)
     if ((e = cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream4, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev3, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_landed, sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(landed)", e);
     if ((e = cudaHostAlloc(&ctx->h_landed, nc_ctx::LANDED_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess)
@@ -96,8 +97,7 @@ void nc_ctx_destroy(nc_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : { &ctx->jobs, &ctx->order, &ctx->counter, &ctx->path, &ctx->mean, &ctx->stdv, &ctx->start,
-                       &ctx->lstd, &ctx->states, &ctx->moves, &ctx->tb, &ctx->cl_col0, &ctx->fb_scratch, &ctx->fb_seqs, &ctx->fb_groups, &ctx->fb_jobs,
-                       &ctx->fb_lz, &ctx->fb_pm, &ctx->fb_st, &ctx->fb_counter, &ctx->fb_mean, &ctx->fb_stdv, &ctx->fb_start, &ctx->fb_lstd,
+                       &ctx->lstd, &ctx->states, &ctx->moves, &ctx->tb, &ctx->cl_col0, &ctx->fb_scratch, &ctx->fb_mean, &ctx->fb_stdv, &ctx->fb_start, &ctx->fb_lstd,
                        &ctx->gen_from_off, &ctx->gen_from_idx, &ctx->gen_from_lp, &ctx->gen_to_off, &ctx->gen_to_idx, &ctx->gen_to_lp,
                        &ctx->gen_bp, &ctx->gen_order, &ctx->gen_counter })
         dev_free(*b);
@@ -111,7 +111,14 @@ void nc_ctx_destroy(nc_ctx* ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
-    for (cudaEvent_t e : ctx->evk) if (e) cudaEventDestroy(e);
+    if (ctx->stream4) { cudaStreamSynchronize(ctx->stream4); cudaStreamDestroy(ctx->stream4); }
+    for (TrainSlot& t : ctx->tslot)
+    {
+        for (DevBuf* b : { &t.d_seqs, &t.d_groups, &t.d_jobs, &t.d_counter, &t.d_lz, &t.d_pm, &t.d_st }) dev_free(*b);
+        for (PinBuf* b : { &t.h_seqs, &t.h_groups, &t.h_jobs, &t.h_lz, &t.h_pm, &t.h_st }) pin_free(*b);
+        for (cudaEvent_t e : t.evk) if (e) cudaEventDestroy(e);
+        if (t.done) cudaEventDestroy(t.done);
+    }
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream3) { cudaStreamSynchronize(ctx->stream3); cudaStreamDestroy(ctx->stream3); }
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);

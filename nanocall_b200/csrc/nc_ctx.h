@@ -17,6 +17,23 @@ struct DevBuf
     size_t cap = 0;
 };
 
+// grow-only page-locked host buffer
+struct PinBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+// One of the two training waves in flight (nc_train.cu): page-locked images of the wave's descriptors (uploaded
+// asynchronously), its statistics on the device and page-locked on the host, and the events around its kernels.
+struct TrainSlot
+{
+    PinBuf h_seqs, h_groups, h_jobs, h_lz, h_pm, h_st;
+    DevBuf d_seqs, d_groups, d_jobs, d_counter, d_lz, d_pm, d_st;
+    cudaEvent_t evk[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // around the four training kernels
+    cudaEvent_t done = nullptr;                                              // the statistics are on the host
+};
+
 struct nc_ctx
 {
     int device = 0;
@@ -44,7 +61,9 @@ struct nc_ctx
     uint32_t cluster_min_events = 2000;   // calls with at most n_sms/2 jobs, each at least this long, give every job a CTA pair
     bool cluster_on = false;              // NC_VIT_CLUSTER=1 switches the cluster kernel on: measured slower than one CTA per
                                           // job (55 ms against 37 ms for a 60 k-event read), see nc_viterbi_alpha.cu
-    DevBuf fb_scratch, fb_seqs, fb_groups, fb_jobs, fb_lz, fb_pm, fb_st, fb_counter, fb_mean, fb_stdv, fb_start, fb_lstd;
+    DevBuf fb_scratch, fb_mean, fb_stdv, fb_start, fb_lstd;
+    TrainSlot tslot[2];
+    cudaStream_t stream4 = nullptr;   // statistics of a training wave back to the host while the next wave computes
     // custom default transition table (nc_ctx_set_default_transitions): in force for jobs / strands whose transition
     // parameters equal gen_default
     bool gen_on = false;
@@ -56,7 +75,6 @@ struct nc_ctx
     size_t fb_scratch_auto = 0;    // the limit derived from the free memory, once
     unsigned host_threads = 1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t evk[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // around the four training kernels of a wave
     double train_ms[4] = { 0, 0, 0, 0 };   // emission, fwbw, pm_stats, st_stats: device time since the last reset
     double train_events = 0, train_launches = 0, train_waves = 0;
     float last_kernel_ms = 0.f;
@@ -96,6 +114,26 @@ inline int dev_reserve(nc_ctx* ctx, DevBuf& b, size_t bytes)
     }
     b.cap = want;
     return NC_OK;
+}
+inline int pin_reserve(nc_ctx* ctx, PinBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return NC_OK;
+    if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        NC_FAIL(ctx, NC_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return NC_OK;
+}
+inline void pin_free(PinBuf& b)
+{
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
 }
 inline void dev_free(DevBuf& b)
 {

@@ -106,7 +106,8 @@ size_t scratch_limit(nc_ctx* ctx)
 }
 
 // train_pm_params after the inner sums (Parameter_Trainer.hpp:297-427).  rows: per event {s0,s1,s2,l0,l1,l2};
-// x/y/t: uncorrected mean, stdv (after the 0 -> 0.01 fix) and start of the same events, in (sequence, event) order.
+// x/y/t: uncorrected mean, stdv (the 0 -> 0.01 fix of Event.hpp:39-43 is applied here) and start of the same events, in
+// (sequence, event) order.
 void finish_pm(size_t n_ev, const float* rows, const float* x, const float* y, const float* t, bool train_drift,
                const nc_pm_params& crt, nc_pm_params& out, int& done)
 {
@@ -118,7 +119,7 @@ void finish_pm(size_t n_ev, const float* rows, const float* x, const float* y, c
     {
         const float* s = rows + 6 * i;
         const float* l = s + 3;
-        float x_i = x[i], y_i = y[i], t_i = t[i];
+        float x_i = x[i], y_i = (y[i] == 0.0f) ? 0.01f : y[i], t_i = t[i];
         A[0][0] += s[0];
         A[0][1] += s[1];
         A[1][1] += s[2];
@@ -223,57 +224,73 @@ struct Wave
     unsigned max_len = 0;
 };
 
-// Upload a wave's descriptors and run emission + fwbw (+ stats).  Event arrays are already on the device.
-int run_wave(nc_ctx* ctx, const Wave& w, const float* d_mean, const float* d_stdv, const float* d_start, const float* d_lstd,
-             bool pm_stats, bool st_stats, std::vector< float >& lz, std::vector< float >& pm_rows, std::vector< float >& st_acc)
+// Waves are pipelined two deep: while the kernels of wave k run, the host builds and queues wave k+1, and only then waits
+// for wave k's statistics and finishes its groups (the 3x3 solves).  submit_wave queues a wave on ctx->stream --
+// descriptors up from the slot's page-locked images, emission + fwbw (+ statistics kernels) -- and, on ctx->stream4
+// behind the last kernel, the statistics back into the slot's page-locked buffers; nothing waits.  collect_wave waits for
+// that copy.  The E|alpha|beta scratch is shared by both slots (stream order keeps wave k+1's kernels behind wave k's);
+// everything a wave returns lives in its slot.  Event arrays are already on the device.
+int submit_wave(nc_ctx* ctx, const Wave& w, TrainSlot& T, const float* d_mean, const float* d_stdv, const float* d_start,
+                const float* d_lstd, bool pm_stats, bool st_stats, int& launches)
 {
     int rc;
     const unsigned ns = (unsigned)w.seqs.size(), ng = (unsigned)w.groups.size();
+    const size_t b_seqs = ns * sizeof(nc::FbSeq), b_groups = ng * sizeof(nc::FbGroup), b_jobs = w.jobs.size() * sizeof(nc::DevJob);
+    const size_t b_lz = ns * sizeof(float), b_pm = w.n_events * 6 * sizeof(float), b_st = (size_t)ng * 6 * sizeof(float);
     if ((rc = dev_reserve(ctx, ctx->fb_scratch, w.scratch_floats * sizeof(float))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->fb_seqs, ns * sizeof(nc::FbSeq))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->fb_groups, std::max(1u, ng) * sizeof(nc::FbGroup))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->fb_jobs, w.jobs.size() * sizeof(nc::DevJob))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->fb_lz, ns * sizeof(float))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->fb_pm, std::max< size_t >(1, w.n_events) * 6 * sizeof(float))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->fb_st, std::max(1u, ng) * 6 * sizeof(float))) != NC_OK) return rc;
-    if ((rc = dev_reserve(ctx, ctx->fb_counter, 2 * sizeof(unsigned))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, T.d_seqs, b_seqs)) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, T.d_groups, std::max< size_t >(1, b_groups))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, T.d_jobs, b_jobs)) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, T.d_lz, b_lz)) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, T.d_pm, std::max< size_t >(1, b_pm))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, T.d_st, std::max< size_t >(1, b_st))) != NC_OK) return rc;
+    if ((rc = dev_reserve(ctx, T.d_counter, 2 * sizeof(unsigned))) != NC_OK) return rc;
+    if ((rc = pin_reserve(ctx, T.h_seqs, b_seqs)) != NC_OK) return rc;
+    if ((rc = pin_reserve(ctx, T.h_groups, std::max< size_t >(1, b_groups))) != NC_OK) return rc;
+    if ((rc = pin_reserve(ctx, T.h_jobs, b_jobs)) != NC_OK) return rc;
+    if ((rc = pin_reserve(ctx, T.h_lz, b_lz)) != NC_OK) return rc;
+    if ((rc = pin_reserve(ctx, T.h_pm, std::max< size_t >(1, b_pm))) != NC_OK) return rc;
+    if ((rc = pin_reserve(ctx, T.h_st, std::max< size_t >(1, b_st))) != NC_OK) return rc;
+    for (int k = 0; k < 5; ++k)
+        if (!T.evk[k]) NC_CUDA(ctx, cudaEventCreate(&T.evk[k]));
+    if (!T.done) NC_CUDA(ctx, cudaEventCreateWithFlags(&T.done, cudaEventDisableTiming));
+    std::memcpy(T.h_seqs.p, w.seqs.data(), b_seqs);
+    if (ng) std::memcpy(T.h_groups.p, w.groups.data(), b_groups);
+    std::memcpy(T.h_jobs.p, w.jobs.data(), b_jobs);
     cudaStream_t s = ctx->stream;
-    NC_CUDA(ctx, cudaMemcpyAsync(ctx->fb_seqs.p, w.seqs.data(), ns * sizeof(nc::FbSeq), cudaMemcpyHostToDevice, s));
-    if (ng) NC_CUDA(ctx, cudaMemcpyAsync(ctx->fb_groups.p, w.groups.data(), ng * sizeof(nc::FbGroup), cudaMemcpyHostToDevice, s));
-    NC_CUDA(ctx, cudaMemcpyAsync(ctx->fb_jobs.p, w.jobs.data(), w.jobs.size() * sizeof(nc::DevJob), cudaMemcpyHostToDevice, s));
-    NC_CUDA(ctx, cudaMemsetAsync(ctx->fb_counter.p, 0, 2 * sizeof(unsigned), s));
+    NC_CUDA(ctx, cudaMemcpyAsync(T.d_seqs.p, T.h_seqs.p, b_seqs, cudaMemcpyHostToDevice, s));
+    if (ng) NC_CUDA(ctx, cudaMemcpyAsync(T.d_groups.p, T.h_groups.p, b_groups, cudaMemcpyHostToDevice, s));
+    NC_CUDA(ctx, cudaMemcpyAsync(T.d_jobs.p, T.h_jobs.p, b_jobs, cudaMemcpyHostToDevice, s));
+    NC_CUDA(ctx, cudaMemsetAsync(T.d_counter.p, 0, 2 * sizeof(unsigned), s));
 
     nc::FbArgs a;
-    a.jobs = (const nc::DevJob*)ctx->fb_jobs.p;
-    a.seqs = (const nc::FbSeq*)ctx->fb_seqs.p;
-    a.groups = (const nc::FbGroup*)ctx->fb_groups.p;
+    a.jobs = (const nc::DevJob*)T.d_jobs.p;
+    a.seqs = (const nc::FbSeq*)T.d_seqs.p;
+    a.groups = (const nc::FbGroup*)T.d_groups.p;
     a.n_seqs = ns;
     a.n_groups = ng;
-    a.next_item = (unsigned*)ctx->fb_counter.p;
+    a.next_item = (unsigned*)T.d_counter.p;
     a.models = ctx->d_models;
     a.mean = d_mean; a.stdv = d_stdv; a.start = d_start; a.log_stdv = d_lstd;
     a.logsum_tbl = ctx->d_logsum_tbl;
     a.train_kmers = ctx->d_train_kmers;
     a.n_train_kmers = ctx->n_train_kmers;
     a.scratch = (float*)ctx->fb_scratch.p;
-    a.log_pr_data = (float*)ctx->fb_lz.p;
-    a.pm_stats = (float*)ctx->fb_pm.p;
-    a.st_stats = (float*)ctx->fb_st.p;
+    a.log_pr_data = (float*)T.d_lz.p;
+    a.pm_stats = (float*)T.d_pm.p;
+    a.st_stats = (float*)T.d_st.p;
     a.log_2pi = (float)std::log(2.0 * M_PI);
     a.log_n_states = std::log((float)NC_N_STATES);
 
     const unsigned tiles = (w.max_len + nc::FB_EV_TILE - 1) / nc::FB_EV_TILE;
-    for (int k = 0; k < 5; ++k)
-        if (!ctx->evk[k]) NC_CUDA(ctx, cudaEventCreate(&ctx->evk[k]));
-    NC_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
-    NC_CUDA(ctx, cudaEventRecord(ctx->evk[0], s));
+    NC_CUDA(ctx, cudaEventRecord(T.evk[0], s));
     nc::emission_kernel<<< dim3(tiles, ns), 512, 0, s >>>(a);
     NC_CUDA(ctx, cudaGetLastError());
-    NC_CUDA(ctx, cudaEventRecord(ctx->evk[1], s));
+    NC_CUDA(ctx, cudaEventRecord(T.evk[1], s));
     const unsigned grid = std::min< unsigned >(ns, 2u * (unsigned)ctx->prop.multiProcessorCount);
     nc::fwbw_kernel<<< grid, 512, nc::fwbw_smem_bytes(), s >>>(a);
     NC_CUDA(ctx, cudaGetLastError());
-    int launches = 2;
+    launches = 2;
     bool any_generic = false;
     for (const auto& q : w.seqs) any_generic = any_generic || q.generic;
     if (any_generic)
@@ -285,42 +302,41 @@ int run_wave(nc_ctx* ctx, const Wave& w, const float* d_mean, const float* d_std
         NC_CUDA(ctx, cudaGetLastError());
         ++launches;
     }
-    NC_CUDA(ctx, cudaEventRecord(ctx->evk[2], s));
+    NC_CUDA(ctx, cudaEventRecord(T.evk[2], s));
     if (pm_stats)
     {
         nc::pm_stats_kernel<<< dim3(tiles, ns), 512, nc::pm_stats_smem_bytes(), s >>>(a);
         NC_CUDA(ctx, cudaGetLastError());
         ++launches;
     }
-    NC_CUDA(ctx, cudaEventRecord(ctx->evk[3], s));
+    NC_CUDA(ctx, cudaEventRecord(T.evk[3], s));
     if (st_stats && ng)
     {
         nc::st_stats_kernel<<< dim3(ng, 2), nc::st_stats_threads(), nc::st_stats_smem_bytes(), s >>>(a);
         NC_CUDA(ctx, cudaGetLastError());
         ++launches;
     }
-    NC_CUDA(ctx, cudaEventRecord(ctx->evk[4], s));
-    NC_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-    lz.resize(ns);
-    NC_CUDA(ctx, cudaMemcpyAsync(lz.data(), ctx->fb_lz.p, ns * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (pm_stats)
-    {
-        pm_rows.resize(w.n_events * 6);
-        NC_CUDA(ctx, cudaMemcpyAsync(pm_rows.data(), ctx->fb_pm.p, pm_rows.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
-    }
-    if (st_stats && ng)
-    {
-        st_acc.resize((size_t)ng * 6);
-        NC_CUDA(ctx, cudaMemcpyAsync(st_acc.data(), ctx->fb_st.p, st_acc.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
-    }
-    NC_CUDA(ctx, cudaStreamSynchronize(s));
+    NC_CUDA(ctx, cudaEventRecord(T.evk[4], s));
+    cudaStream_t c = ctx->stream4;
+    NC_CUDA(ctx, cudaStreamWaitEvent(c, T.evk[4], 0));
+    NC_CUDA(ctx, cudaMemcpyAsync(T.h_lz.p, T.d_lz.p, b_lz, cudaMemcpyDeviceToHost, c));
+    if (pm_stats && b_pm) NC_CUDA(ctx, cudaMemcpyAsync(T.h_pm.p, T.d_pm.p, b_pm, cudaMemcpyDeviceToHost, c));
+    if (st_stats && ng) NC_CUDA(ctx, cudaMemcpyAsync(T.h_st.p, T.d_st.p, b_st, cudaMemcpyDeviceToHost, c));
+    NC_CUDA(ctx, cudaEventRecord(T.done, c));
+    return NC_OK;
+}
+
+// Wait for a submitted wave; its statistics are then in T.h_lz / T.h_pm / T.h_st.  ctx->last_kernel_ms = its device time.
+int collect_wave(nc_ctx* ctx, const Wave& w, TrainSlot& T, int launches)
+{
+    NC_CUDA(ctx, cudaEventSynchronize(T.done));
     float ms = 0.f;
-    NC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    NC_CUDA(ctx, cudaEventElapsedTime(&ms, T.evk[0], T.evk[4]));
     ctx->last_kernel_ms = ms;
     for (int k = 0; k < 4; ++k)
     {
         float kms = 0.f;
-        NC_CUDA(ctx, cudaEventElapsedTime(&kms, ctx->evk[k], ctx->evk[k + 1]));
+        NC_CUDA(ctx, cudaEventElapsedTime(&kms, T.evk[k], T.evk[k + 1]));
         ctx->train_ms[k] += kms;
     }
     ctx->train_events += (double)w.n_events;
@@ -329,12 +345,16 @@ int run_wave(nc_ctx* ctx, const Wave& w, const float* d_mean, const float* d_std
     return NC_OK;
 }
 
-int upload_events(nc_ctx* ctx, size_t total, const float* mean, const float* stdv, const float* start,
-                  std::vector< float >& y_fixed)
+// after a failure with work in flight: nothing may still be running against the context's buffers when the call returns
+void drain_train(nc_ctx* ctx)
+{
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream4) cudaStreamSynchronize(ctx->stream4);
+}
+
+int upload_events(nc_ctx* ctx, size_t total, const float* mean, const float* stdv, const float* start)
 {
     int rc;
-    y_fixed.resize(total);
-    for (size_t i = 0; i < total; ++i) y_fixed[i] = (stdv[i] == 0.0f) ? 0.01f : stdv[i];
     if ((rc = dev_reserve(ctx, ctx->fb_mean, total * sizeof(float))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->fb_stdv, total * sizeof(float))) != NC_OK) return rc;
     if ((rc = dev_reserve(ctx, ctx->fb_start, total * sizeof(float))) != NC_OK) return rc;
@@ -353,7 +373,7 @@ double g_train_t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 void nc_train_timing_report()
 {
     if (!std::getenv("NC_TRAIN_TIMING")) return;
-    std::fprintf(stderr, "nc_train_round_batch host time: upload %.3f s, scratch_limit %.3f, wave build %.3f, fill_job %.3f, run_wave (launch+kernels+copies) %.3f, finish %.3f, calls %.0f\n",
+    std::fprintf(stderr, "nc_train_round_batch host time: upload %.3f s, scratch_limit %.3f, wave build %.3f, fill_job %.3f, waiting for a wave %.3f, finish %.3f, calls %.0f\n",
                  g_train_t[6], g_train_t[7], g_train_t[1], g_train_t[2], g_train_t[3], g_train_t[4], g_train_t[5]);
 }
 
@@ -367,8 +387,7 @@ int nc_fwbw(nc_ctx* ctx, int32_t model_id, const nc_pm_params* pm, const nc_st_p
     if (model_id < 0 || model_id >= (int)ctx->models.size()) NC_FAIL(ctx, NC_ERR_ARG, "nc_fwbw: unknown model id %d", model_id);
     int rc;
     if ((rc = ensure_train_tables(ctx)) != NC_OK) return rc;
-    std::vector< float > yfix;
-    if ((rc = upload_events(ctx, n_events, mean, stdv, start, yfix)) != NC_OK) return rc;
+    if ((rc = upload_events(ctx, n_events, mean, stdv, start)) != NC_OK) return rc;
     Wave w;
     w.jobs.resize(1);
     fill_job(w.jobs[0], model_id, *pm, *st);
@@ -380,15 +399,17 @@ int nc_fwbw(nc_ctx* ctx, int32_t model_id, const nc_pm_params* pm, const nc_st_p
     w.scratch_floats = (size_t)3 * n_events * NC_N_STATES;
     w.n_events = n_events;
     w.max_len = n_events;
-    std::vector< float > lz, pmr, sta;
-    if ((rc = run_wave(ctx, w, (const float*)ctx->fb_mean.p, (const float*)ctx->fb_stdv.p, (const float*)ctx->fb_start.p,
-                       nullptr, false, false, lz, pmr, sta)) != NC_OK)
-        return rc;
+    int launches = 0;
+    TrainSlot& T = ctx->tslot[0];
+    rc = submit_wave(ctx, w, T, (const float*)ctx->fb_mean.p, (const float*)ctx->fb_stdv.p, (const float*)ctx->fb_start.p,
+                     nullptr, false, false, launches);
+    if (rc == NC_OK) rc = collect_wave(ctx, w, T, launches);
+    if (rc != NC_OK) { drain_train(ctx); return rc; }
     const size_t cells = (size_t)n_events * NC_N_STATES;
     const float* sc = (const float*)ctx->fb_scratch.p;
     if (alpha) NC_CUDA(ctx, cudaMemcpy(alpha, sc + cells, cells * sizeof(float), cudaMemcpyDeviceToHost));
     if (beta) NC_CUDA(ctx, cudaMemcpy(beta, sc + 2 * cells, cells * sizeof(float), cudaMemcpyDeviceToHost));
-    if (log_pr_data) *log_pr_data = lz[0];
+    if (log_pr_data) *log_pr_data = static_cast< const float* >(T.h_lz.p)[0];
     return NC_OK;
 }
 
@@ -430,19 +451,15 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
     g_train_t[5] += 1;
     const uint64_t base = ev_off[0];
     const size_t total = ev_off[n_seqs] - base;
-    std::vector< float > yfix;
-    if ((rc = upload_events(ctx, total, mean + base, stdv + base, start + base, yfix)) != NC_OK) return rc;
+    if ((rc = upload_events(ctx, total, mean + base, stdv + base, start + base)) != NC_OK) return rc;
     lap(6, tl);
     const size_t limit_floats = scratch_limit(ctx) / sizeof(float);
     lap(7, tl);
+    if (!ctx->stream4) NC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream4, cudaStreamNonBlocking));
 
-    uint32_t g0 = 0;
-    std::vector< float > lz, pm_rows, st_acc;
-    float kernel_ms = 0.f;   // device time of the call = sum over its waves
-    while (g0 < n_groups)
-    {
-        // ---- a wave: consecutive groups whose slabs fit the scratch pool
-        Wave w;
+    // ---- a wave: consecutive groups whose slabs fit the scratch pool
+    auto build_wave = [&](Wave& w, uint32_t g0) -> uint32_t {
+        w = Wave();
         uint32_t g1 = g0;
         while (g1 < n_groups)
         {
@@ -485,13 +502,13 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
             for (int st = 0; st < 2; ++st) fill_job(w.jobs[2 * k + st], in[g0 + k].model_id[st], in[g0 + k].pm, in[g0 + k].st[st]);
         });
         lap(2, tl);
-        if ((rc = run_wave(ctx, w, (const float*)ctx->fb_mean.p, (const float*)ctx->fb_stdv.p, (const float*)ctx->fb_start.p,
-                           nullptr, opts->train_scaling != 0, opts->train_transitions != 0,
-                           lz, pm_rows, st_acc)) != NC_OK)
-            return rc;
-        kernel_ms += ctx->last_kernel_ms;
-        lap(3, tl);
-        // ---- finish every group of the wave on the host (train_one_round, :541-579)
+        return g1;
+    };
+    // ---- finish every group of a collected wave on the host (train_one_round, :541-579)
+    auto finish_wave = [&](const Wave& w, const TrainSlot& T, uint32_t g0, uint32_t g1) {
+        const float* lz = static_cast< const float* >(T.h_lz.p);
+        const float* pm_rows = static_cast< const float* >(T.h_pm.p);
+        const float* st_acc = static_cast< const float* >(T.h_st.p);
         parallel_for(g1 - g0, ctx->host_threads, [&](size_t gk)
         {
             const uint32_t g = g0 + (uint32_t)gk;
@@ -511,19 +528,49 @@ int nc_train_round_batch(nc_ctx* ctx, uint32_t n_groups, const uint32_t* seq_off
                 for (unsigned q = G.seq_begin; q < G.seq_end; ++q) n_ev += w.seqs[q].n_events;
                 // the group's events are contiguous in (sequence, event) order both in pm_rows and in the inputs
                 int done = 0;
-                finish_pm(n_ev, pm_rows.data() + 6 * first.ev_out, mean + base + first.ev_off, yfix.data() + first.ev_off,
+                finish_pm(n_ev, pm_rows + 6 * first.ev_out, mean + base + first.ev_off, stdv + base + first.ev_off,
                           start + base + first.ev_off, opts->train_drift != 0, in[g].pm, o.pm, done);
                 o.done = done;
                 if (done) return;  // new_st_params = crt_st_params (:566-570)
             }
             if (opts->train_transitions)
             {
-                o.st[0] = finish_st(st_acc.data() + (size_t)(g - g0) * 6);
-                o.st[1] = finish_st(st_acc.data() + (size_t)(g - g0) * 6 + 3);
+                o.st[0] = finish_st(st_acc + (size_t)(g - g0) * 6);
+                o.st[1] = finish_st(st_acc + (size_t)(g - g0) * 6 + 3);
             }
         });
         lap(4, tl);
-        g0 = g1;
+    };
+
+    // ---- two waves in flight: wave k+1 is built and queued while wave k's kernels run, then wave k is collected and finished
+    Wave wv[2];
+    uint32_t wg0[2] = { 0, 0 }, wg1[2] = { 0, 0 };
+    int wl[2] = { 0, 0 };
+    float kernel_ms = 0.f;   // device time of the call = sum over its waves
+    auto submit = [&](int k) -> int {
+        return submit_wave(ctx, wv[k], ctx->tslot[k], (const float*)ctx->fb_mean.p, (const float*)ctx->fb_stdv.p,
+                           (const float*)ctx->fb_start.p, nullptr, opts->train_scaling != 0, opts->train_transitions != 0, wl[k]);
+    };
+    int cur = 0;
+    wg0[0] = 0;
+    wg1[0] = build_wave(wv[0], 0);
+    if ((rc = submit(0)) != NC_OK) { drain_train(ctx); return rc; }
+    for (;;)
+    {
+        const int nxt = cur ^ 1;
+        const bool more = wg1[cur] < n_groups;
+        if (more)
+        {
+            wg0[nxt] = wg1[cur];
+            wg1[nxt] = build_wave(wv[nxt], wg0[nxt]);
+            if ((rc = submit(nxt)) != NC_OK) { drain_train(ctx); return rc; }
+        }
+        if ((rc = collect_wave(ctx, wv[cur], ctx->tslot[cur], wl[cur])) != NC_OK) { drain_train(ctx); return rc; }
+        kernel_ms += ctx->last_kernel_ms;
+        lap(3, tl);
+        finish_wave(wv[cur], ctx->tslot[cur], wg0[cur], wg1[cur]);
+        if (!more) break;
+        cur = nxt;
     }
     ctx->last_kernel_ms = kernel_ms;
     return NC_OK;
@@ -539,7 +586,8 @@ int nc_ctx_reserve(nc_ctx* ctx, uint64_t train_events, uint64_t viterbi_events)
         if ((rc = ensure_train_tables(ctx)) != NC_OK) return rc;
         const size_t want = std::min< size_t >(scratch_limit(ctx), (size_t)train_events * 3 * NC_N_STATES * sizeof(float));
         if ((rc = dev_reserve(ctx, ctx->fb_scratch, want)) != NC_OK) return rc;
-        if ((rc = dev_reserve(ctx, ctx->fb_pm, (size_t)train_events * 6 * sizeof(float))) != NC_OK) return rc;
+        // (the statistics buffers of the two wave slots are sized by the waves themselves: a wave is at most
+        // scratch_limit / 48 KB events)
         for (DevBuf* b : { &ctx->fb_mean, &ctx->fb_stdv, &ctx->fb_start })
             if ((rc = dev_reserve(ctx, *b, (size_t)train_events * sizeof(float))) != NC_OK) return rc;
     }
