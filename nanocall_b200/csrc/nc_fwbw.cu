@@ -293,24 +293,37 @@ static_assert((FB_THREADS - 96) == 8 * PM_JT, "13 producer warps = 8 x PM_JT");
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
-// E[seq][i][j]
+// E[seq][i][j].  One CTA = EM_TILE events of one sequence: the event scalars (drift-corrected mean, stdv, 3 log stdv,
+// 1/stdv: a logf and a reciprocal each) are computed once per CTA by its first threads, not by every thread, and the
+// scaled state constants of a thread (scale_state: divisions and logarithms) are spread over EM_TILE events.
 __global__ void __launch_bounds__(FB_THREADS) emission_kernel(const FbArgs a)
 {
+    __shared__ float4 ev_s[EM_TILE];   // {x, y, 3 log y, 1/y}
     const unsigned seq = blockIdx.y;
     const FbSeq& Q = a.seqs[seq];
-    const unsigned i0 = blockIdx.x * FB_EV_TILE;
+    const unsigned i0 = blockIdx.x * EM_TILE;
     if (i0 >= Q.n_events) return;
     const DevJob& J = a.jobs[Q.job];
     const int t = threadIdx.x;
-    const unsigned j0 = FB_SPT * t;
+    const unsigned j0 = 4 * t;   // a warp's float4 stores are 512 contiguous bytes (full sectors); second half: + 2048
     const float* M = a.models + (size_t)J.model * MODEL_FLOATS;
     float* E = a.scratch + Q.slab + 0 * (size_t)Q.n_events * NC_N_STATES;
-    const unsigned i1 = min(i0 + FB_EV_TILE, Q.n_events);
+    const unsigned i1 = min(i0 + EM_TILE, Q.n_events);
+    if (i0 + t < i1)
+    {
+        const unsigned long long e = Q.ev_off + i0 + t;
+        const float stdv = __ldg(a.stdv + e);
+        const float y = (stdv == 0.0f) ? 0.01f : stdv;                                  // Event.hpp:39-42
+        const float x = __fsub_rn(__ldg(a.mean + e), __fmul_rn(J.drift, __ldg(a.start + e)));  // Event.hpp:81
+        const float ly3 = __fmul_rn(3.0f, a.log_stdv ? __ldg(a.log_stdv + e) : nc_logf(y));
+        ev_s[t] = make_float4(x, y, ly3, __frcp_rn(y));
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int half = 0; half < 2; ++half)
     {
         StateParams P[4];
-        const unsigned jb = j0 + 4 * half;
+        const unsigned jb = j0 + (NC_N_STATES / 2) * half;
         {
             const float4 lm = __ldg(reinterpret_cast< const float4* >(M + 0 * NC_N_STATES + jb));
             const float4 ls = __ldg(reinterpret_cast< const float4* >(M + 1 * NC_N_STATES + jb));
@@ -323,20 +336,16 @@ __global__ void __launch_bounds__(FB_THREADS) emission_kernel(const FbArgs a)
             P[2] = scale_state(lm.z, ls.z, sm.z, sl.z, ll.z, lsl.z, J, a.log_2pi);
             P[3] = scale_state(lm.w, ls.w, sm.w, sl.w, ll.w, lsl.w, J, a.log_2pi);
         }
-        for (unsigned i = i0; i < i1; ++i)
+        float* Ei = E + (size_t)i0 * NC_N_STATES + jb;
+        for (unsigned i = i0; i < i1; ++i, Ei += NC_N_STATES)
         {
-            const unsigned long long e = Q.ev_off + i;
-            const float stdv = __ldg(a.stdv + e);
-            const float y = (stdv == 0.0f) ? 0.01f : stdv;                                  // Event.hpp:39-42
-            const float x = __fsub_rn(__ldg(a.mean + e), __fmul_rn(J.drift, __ldg(a.start + e)));  // Event.hpp:81
-            const float ly3 = __fmul_rn(3.0f, a.log_stdv ? __ldg(a.log_stdv + e) : nc_logf(y));
-            const float ry = __frcp_rn(y);
+            const float4 ev = ev_s[i - i0];
             float4 o;
-            o.x = emission(P[0], x, y, ly3, ry, a.log_2pi);
-            o.y = emission(P[1], x, y, ly3, ry, a.log_2pi);
-            o.z = emission(P[2], x, y, ly3, ry, a.log_2pi);
-            o.w = emission(P[3], x, y, ly3, ry, a.log_2pi);
-            *reinterpret_cast< float4* >(E + (size_t)i * NC_N_STATES + jb) = o;
+            o.x = emission(P[0], ev.x, ev.y, ev.z, ev.w, a.log_2pi);
+            o.y = emission(P[1], ev.x, ev.y, ev.z, ev.w, a.log_2pi);
+            o.z = emission(P[2], ev.x, ev.y, ev.z, ev.w, a.log_2pi);
+            o.w = emission(P[3], ev.x, ev.y, ev.z, ev.w, a.log_2pi);
+            *reinterpret_cast< float4* >(Ei) = o;
         }
     }
 }

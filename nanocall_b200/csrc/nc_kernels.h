@@ -72,7 +72,11 @@ unsigned viterbi_alpha_max_forward_ctas();   // bound of the allocator's extent 
 void viterbi_alpha_colalloc_init(void* host_image, unsigned pool_columns);
 
 // ---- Forward/Backward + trainer statistics
-enum { FB_EV_TILE = 16 };
+enum { FB_EV_TILE = 16 };   // events per CTA of pm_stats_kernel
+#ifndef NC_EM_TILE
+#define NC_EM_TILE 50
+#endif
+enum { EM_TILE = NC_EM_TILE };   // events per CTA of emission_kernel
 
 struct FbSeq
 {

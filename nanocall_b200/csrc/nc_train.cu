@@ -284,7 +284,7 @@ int submit_wave(nc_ctx* ctx, const Wave& w, TrainSlot& T, const float* d_mean, c
 
     const unsigned tiles = (w.max_len + nc::FB_EV_TILE - 1) / nc::FB_EV_TILE;
     NC_CUDA(ctx, cudaEventRecord(T.evk[0], s));
-    nc::emission_kernel<<< dim3(tiles, ns), 512, 0, s >>>(a);
+    nc::emission_kernel<<< dim3((w.max_len + nc::EM_TILE - 1) / nc::EM_TILE, ns), 512, 0, s >>>(a);
     NC_CUDA(ctx, cudaGetLastError());
     NC_CUDA(ctx, cudaEventRecord(T.evk[1], s));
     const unsigned grid = std::min< unsigned >(ns, 2u * (unsigned)ctx->prop.multiProcessorCount);
