@@ -74,6 +74,9 @@ __device__ __forceinline__ float fold_logsum_in_order(float acc, const int n, Ge
 // a + t is the result; otherwise the recomputed indices are the next guess (the first unconfirmed lane is certainly
 // right then).  After three rounds, or when a term exceeds the running value (start of a chain), the block is folded
 // term by term.  lst: 40 floats, 16-byte aligned, private to the warp.
+#ifndef NC_FB_OPAQUE
+#define NC_FB_OPAQUE 1
+#endif
 #ifndef NC_ST_EXP
 #define NC_ST_EXP 0   // timing experiments only: 1 = no phase-2 arithmetic, 2 = no fold; anything but 0 is not a product build
 #endif
@@ -358,7 +361,12 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
     const int t = threadIdx.x;
     const int lane = t & 31;
     for (int q = t; q < fb::TBL_N; q += FB_THREADS) sm.tbl[q] = a.logsum_tbl[q];   // entry 15999 is 0 (nc_train.cu)
-    const fb::TblSmem tbl = fb::make_tbl_smem(sm.tbl);
+    fb::TblSmem tbl = fb::make_tbl_smem(sm.tbl);
+#if NC_FB_OPAQUE
+    // ptxas otherwise rebuilds the constant from the CTA's shared-window base (S2UR, UMOV, ULEA, IMAD, I2FP, FMUL, FADD:
+    // seven instructions) in front of every group of folds instead of holding it in a register
+    asm volatile("" : "+f"(tbl.magic));
+#endif
 
     for (;;)
     {
@@ -381,6 +389,11 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
         {
             fb::FwdConst C;
             fb::fwd_const_init(C, fb::fwd_logical_thread(t), sm.lut);
+#if NC_FB_OPAQUE
+            // (the same for the per-thread order flags: recomputed from threadIdx inside the column loops, ~20 integer
+            // instructions per one-step slot, unless their origin is hidden from the compiler)
+            asm volatile("" : "+r"(C.flags), "+r"(C.pos), "+r"(C.sS), "+r"(C.c));
+#endif
             const unsigned j0 = FB_SPT * (unsigned)C.u;
             const int p0 = cphys((int)j0), p1 = cphys((int)j0 + 4);
             float own[8];
@@ -441,6 +454,9 @@ __global__ void __launch_bounds__(FB_THREADS, 2) fwbw_kernel(const FbArgs a)
                 const unsigned c0 = __shfl_sync(FULL, code, 0);
                 if (__all_sync(FULL, code == c0)) C.paths |= c0 << (3 * k);
             }
+#if NC_FB_OPAQUE
+            asm volatile("" : "+r"(C.flags), "+r"(C.paths), "+r"(C.smask[0]), "+r"(C.smask[1]));
+#endif
             // beta[n-1] = 0
 #pragma unroll
             for (int k = 0; k < FB_SPT; ++k)
