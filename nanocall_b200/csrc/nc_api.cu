@@ -108,6 +108,7 @@ void nc_ctx_destroy(nc_ctx* ctx)
     if (ctx->h_abort) cudaFreeHost(ctx->h_abort);
     if (ctx->d_logsum_tbl) cudaFree(ctx->d_logsum_tbl);
     if (ctx->d_train_kmers) cudaFree(ctx->d_train_kmers);
+    if (ctx->d_pm_consts) cudaFree(ctx->d_pm_consts);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);

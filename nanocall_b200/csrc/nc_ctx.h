@@ -69,6 +69,8 @@ struct nc_ctx
     bool gen_on = false;
     nc_st_params gen_default{ 0.f, 0.f };
     DevBuf gen_from_off, gen_from_idx, gen_from_lp, gen_to_off, gen_to_idx, gen_to_lp, gen_bp, gen_order, gen_counter;
+    float* d_pm_consts = nullptr;     // pm_stats_kernel's per-state constants of every registered model (FbArgs::pm_consts)
+    size_t pm_consts_models = 0;      // how many models the table covers
     unsigned* d_train_kmers = nullptr;
     unsigned n_train_kmers = 0;
     size_t fb_scratch_limit = 0;  // bytes of E|alpha|beta slabs per wave (0 = pick from free memory)

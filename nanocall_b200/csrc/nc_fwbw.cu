@@ -287,7 +287,8 @@ struct StSmem
 constexpr float PM_SCALE = 18446744073709551616.0f;
 constexpr int PM_EV = 16;                 // events per CTA of pm_stats_kernel (= FB_EV_TILE)
 constexpr int PM_CHAINS = PM_EV * 6;      // 96 serial sums = the lanes of three warps
-constexpr int PM_ROW = PM_CHAINS + 1;     // row stride of the term buffer: producer lanes (consecutive states) hit different banks
+constexpr int PM_ROW = PM_CHAINS + 2;     // row stride of the term buffer: even (the producers store float2), and the 16 lanes of a
+                                          // half warp (consecutive states) cover all 32 banks
 constexpr int PM_JT = 52;                 // states per tile: 13 producer warps x 32 = 8 event-pairs x 52 states
 constexpr int PM_TILES = (NC_N_STATES + PM_JT - 1) / PM_JT;   // 79
 static_assert(FB_EV_TILE == PM_EV, "pm_stats grid uses FB_EV_TILE");
@@ -508,7 +509,6 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
     const unsigned n = Q.n_events;
     const DevJob& J = a.jobs[Q.job];
     const int t = threadIdx.x;
-    const float* M = a.models + (size_t)J.model * MODEL_FLOATS;
     const float* AL = a.scratch + Q.slab + 1 * (size_t)n * NC_N_STATES;
     const float* BE = a.scratch + Q.slab + 2 * (size_t)n * NC_N_STATES;
     const float logz = a.log_pr_data[seq];
@@ -531,66 +531,61 @@ __global__ void __launch_bounds__(FB_THREADS) pm_stats_kernel(const FbArgs a)
     }
     else
     {
-        // ---- producers: thread p handles state jt*52 + (p % 52) for the events (p / 52) and (p / 52) + 8
+        // ---- producers: thread p handles state tile*52 + (p % 52) for the events (p / 52) and (p / 52) + 8.
+        // Everything that does not change from tile to tile is a pointer stepped by 52 states or a flag set up here, and
+        // the state's constants (mu, sigma^2, 1/sigma^2, eta, 1/eta, lambda: two correctly rounded reciprocals) come
+        // from a per-model table (FbArgs::pm_consts) instead of being rebuilt by every CTA for every pair of events.
         const int p = t - PM_CHAINS;
         const int jl = p % PM_JT, eg = p / PM_JT;   // eg = 0..7
+        const bool on0 = (unsigned)eg < n_ev, on1 = (unsigned)eg + 8u < n_ev;
+        const float* pA = AL + (size_t)(i0 + eg) * NC_N_STATES + jl;   // event eg; event eg + 8 lies 8 rows further
+        const float* pB = BE + (size_t)(i0 + eg) * NC_N_STATES + jl;
+        constexpr int ROW8 = 8 * NC_N_STATES;
+        const float4* pC = a.pm_consts + ((size_t)J.model * NC_N_STATES + jl) * 2;
+        float* T0 = term + jl * PM_ROW + 6 * eg;                       // this thread's six terms of event eg, buffer 0
+        constexpr int BUF = PM_JT * PM_ROW;
         // alpha + beta of the NEXT tile are loaded while the current one is computed (the loads come from HBM: every
         // tile touches a new 208-byte piece of each of the 16 event rows)
-        float al[2], be[2];
-        auto load_tile = [&](int tile, float (&a2)[2], float (&b2)[2]) {
-            const int j = tile * PM_JT + jl;
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-            {
-                const unsigned ev = (unsigned)(eg + 8 * r);
-                a2[r] = b2[r] = 0.f;
-                if (tile < PM_TILES && j < (int)NC_N_STATES && ev < n_ev)
-                {
-                    const size_t o = (size_t)(i0 + ev) * NC_N_STATES + j;
-                    a2[r] = __ldcs(AL + o);
-                    b2[r] = __ldcs(BE + o);
-                }
-            }
+        float al0 = 0.f, be0 = 0.f, al1 = 0.f, be1 = 0.f;
+        if (on0) { al0 = __ldcs(pA); be0 = __ldcs(pB); }
+        if (on1) { al1 = __ldcs(pA + ROW8); be1 = __ldcs(pB + ROW8); }
+        auto terms = [&](const float4& c0, const float4& c1, float al, float be, float* R) {
+            // the posterior, scaled by 2^64 (exact): every term below stays in the normal range, so the correctly rounded
+            // divisions are three instructions (div_rn) instead of the IEEE division's denormal slow path, which two
+            // thirds of the kernel's instructions used to be
+            const float pst = __fmul_rn(nc_expf(__fsub_rn(__fadd_rn(al, be), logz)), PM_SCALE);
+            const float ts0 = div_rn(pst, c0.y, c0.z);        // / sigma^2
+            const float ts1 = __fmul_rn(ts0, c0.x);           // * mu
+            const float ts2 = __fmul_rn(ts1, c0.x);
+            const float tl0 = __fmul_rn(pst, c1.y);           // * lambda
+            const float tl1 = div_rn(tl0, c0.w, c1.x);        // / eta
+            const float tl2 = div_rn(tl1, c0.w, c1.x);
+            *reinterpret_cast< float2* >(R) = make_float2(ts0, ts1);
+            *reinterpret_cast< float2* >(R + 2) = make_float2(ts2, tl0);
+            *reinterpret_cast< float2* >(R + 4) = make_float2(tl1, tl2);
         };
-        load_tile(0, al, be);
-        for (int tile = 0; tile < PM_TILES; ++tile)
+        const float2 Z2 = make_float2(0.f, 0.f);
+        int j = jl;
+#pragma unroll 2
+        for (int tile = 0; tile < PM_TILES; ++tile, j += PM_JT, pA += PM_JT, pB += PM_JT, pC += 2 * PM_JT)
         {
-            const int j = tile * PM_JT + jl;
-            float aln[2], ben[2];
-            load_tile(tile + 1, aln, ben);
-            float* T = term + (size_t)(tile & 1) * PM_JT * PM_ROW + jl * PM_ROW;
+            float aln0 = 0.f, ben0 = 0.f, aln1 = 0.f, ben1 = 0.f;
+            if (j + PM_JT < (int)NC_N_STATES)
+            {
+                if (on0) { aln0 = __ldcs(pA + PM_JT); ben0 = __ldcs(pB + PM_JT); }
+                if (on1) { aln1 = __ldcs(pA + PM_JT + ROW8); ben1 = __ldcs(pB + PM_JT + ROW8); }
+            }
+            float* R = T0 + (tile & 1) * BUF;
             if (j < (int)NC_N_STATES)
             {
-                const float mu = __ldg(M + 0 * NC_N_STATES + j);
-                const float sg = __ldg(M + 1 * NC_N_STATES + j);
-                const float sg2 = __fmul_rn(sg, sg);
-                const float eta = __ldg(M + 2 * NC_N_STATES + j);
-                const float lam = __ldg(M + 3 * NC_N_STATES + j);
-                const float rsg2 = __frcp_rn(sg2), reta = __frcp_rn(eta);
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-                {
-                    const unsigned ev = (unsigned)(eg + 8 * r);
-                    float ts0 = 0.f, ts1 = 0.f, ts2 = 0.f, tl0 = 0.f, tl1 = 0.f, tl2 = 0.f;
-                    if (ev < n_ev)
-                    {
-                        // the posterior, scaled by 2^64 (exact): every term below stays in the normal range, so the
-                        // correctly rounded divisions are three instructions (div_rn) instead of the IEEE division's
-                        // denormal slow path, which two thirds of the kernel's instructions used to be
-                        const float pst = __fmul_rn(nc_expf(__fsub_rn(__fadd_rn(al[r], be[r]), logz)), PM_SCALE);
-                        ts0 = div_rn(pst, sg2, rsg2);
-                        ts1 = __fmul_rn(ts0, mu);
-                        ts2 = __fmul_rn(ts1, mu);
-                        tl0 = __fmul_rn(pst, lam);
-                        tl1 = div_rn(tl0, eta, reta);
-                        tl2 = div_rn(tl1, eta, reta);
-                    }
-                    float* R = T + 6 * ev;
-                    R[0] = ts0; R[1] = ts1; R[2] = ts2; R[3] = tl0; R[4] = tl1; R[5] = tl2;
-                }
+                const float4 c0 = __ldg(pC), c1 = __ldg(pC + 1);
+                if (on0) terms(c0, c1, al0, be0, R);
+                else { *reinterpret_cast< float2* >(R) = Z2; *reinterpret_cast< float2* >(R + 2) = Z2; *reinterpret_cast< float2* >(R + 4) = Z2; }
+                if (on1) terms(c0, c1, al1, be1, R + 48);
+                else { *reinterpret_cast< float2* >(R + 48) = Z2; *reinterpret_cast< float2* >(R + 50) = Z2; *reinterpret_cast< float2* >(R + 52) = Z2; }
             }
             __syncthreads();   // publishes tile `tile`; the folding lanes are at most one tile behind
-            al[0] = aln[0]; al[1] = aln[1]; be[0] = ben[0]; be[1] = ben[1];
+            al0 = aln0; be0 = ben0; al1 = aln1; be1 = ben1;
         }
     }
 }

@@ -106,6 +106,7 @@ struct FbArgs
     unsigned n_groups;
     unsigned* next_item;
     const float* models;
+    const float4* pm_consts;       // per model and state {mu, sigma^2, 1/sigma^2, eta}, {1/eta, lambda, 0, 0} (unscaled model)
     const float* mean;
     const float* stdv;
     const float* start;

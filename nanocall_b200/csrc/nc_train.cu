@@ -29,6 +29,28 @@ int ensure_train_tables(nc_ctx* ctx)
     // every entry point that touches the device selects the context's GPU first: the caller's thread may have
     // another one current (several contexts driven from one thread, or a host framework that switched devices)
     NC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->pm_consts_models != ctx->models.size())
+    {
+        // train_pm_params' per-state constants of the UNSCALED models (Parameter_Trainer.hpp:270-290): sigma^2 and the
+        // correctly rounded reciprocals the kernel's three-instruction divisions start from (1.0f / x in IEEE float)
+        const size_t nm = ctx->models.size();
+        std::vector< float > pc(nm * NC_N_STATES * 8, 0.f);
+        for (size_t m = 0; m < nm; ++m)
+            for (unsigned j = 0; j < NC_N_STATES; ++j)
+            {
+                const nc::HostModel& M = ctx->models[m];
+                float* q = pc.data() + (m * NC_N_STATES + j) * 8;
+                const float sg2 = M.level_stdv[j] * M.level_stdv[j];
+                q[0] = M.level_mean[j]; q[1] = sg2; q[2] = 1.0f / sg2; q[3] = M.sd_mean[j];
+                q[4] = 1.0f / M.sd_mean[j]; q[5] = M.sd_lambda[j];
+            }
+        NC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_pm_consts) { cudaFree(ctx->d_pm_consts); ctx->d_pm_consts = nullptr; }
+        ctx->pm_consts_models = 0;
+        NC_CUDA(ctx, cudaMalloc(&ctx->d_pm_consts, std::max< size_t >(1, pc.size()) * sizeof(float)));
+        if (!pc.empty()) NC_CUDA(ctx, cudaMemcpy(ctx->d_pm_consts, pc.data(), pc.size() * sizeof(float), cudaMemcpyHostToDevice));
+        ctx->pm_consts_models = nm;
+    }
     if (ctx->d_logsum_tbl && ctx->d_train_kmers) return NC_OK;
     if (!ctx->d_logsum_tbl)
     {
@@ -271,6 +293,7 @@ int submit_wave(nc_ctx* ctx, const Wave& w, TrainSlot& T, const float* d_mean, c
     a.n_groups = ng;
     a.next_item = (unsigned*)T.d_counter.p;
     a.models = ctx->d_models;
+    a.pm_consts = reinterpret_cast< const float4* >(ctx->d_pm_consts);
     a.mean = d_mean; a.stdv = d_stdv; a.start = d_start; a.log_stdv = d_lstd;
     a.logsum_tbl = ctx->d_logsum_tbl;
     a.train_kmers = ctx->d_train_kmers;
