@@ -4,7 +4,9 @@
 // -ffp-contract=off: the reference's Release build is baseline x86-64 (no FMA).
 #include "nc_internal.h"
 
+#include <algorithm>
 #include <cmath>
+#include <functional>
 #include <set>
 #include <queue>
 #include <cstring>
@@ -130,8 +132,13 @@ int nc_plan_dispatch_order(uint32_t n_jobs, const uint32_t* lens, uint64_t pool_
     for (uint32_t k = 0; k < n_jobs; ++k) perm[k] = k;
     if (n_jobs == 0 || n_workers == 0 || n_jobs <= n_workers) return 0;
     const uint64_t pool_cols = (uint64_t)((double)pool_columns * 0.9);
+    // the first wave = the n_workers longest jobs, wherever they are in lens[] (the caller need not pass them sorted)
     uint64_t need_first = 0;
-    for (uint32_t k = 0; k < n_workers; ++k) need_first += lens[k];
+    {
+        std::vector< uint32_t > top(lens, lens + n_jobs);
+        std::nth_element(top.begin(), top.begin() + n_workers, top.end(), std::greater< uint32_t >());
+        for (uint32_t k = 0; k < n_workers; ++k) need_first += top[k];
+    }
     if (need_first * 11 / 10 <= pool_cols) return 0;
     std::multiset< std::pair< uint32_t, uint32_t > > remaining;   // (length, index): ascending
     for (uint32_t k = 0; k < n_jobs; ++k) remaining.insert({ lens[k], k });

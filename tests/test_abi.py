@@ -106,3 +106,17 @@ def test_dispatch_order_planner():
     p2 = np.zeros(small.size, np.uint32)
     assert lib.nc_plan_dispatch_order(small.size, small.ctypes.data, C.c_uint64(pool), workers, p2.ctypes.data) == 0
     assert np.array_equal(p2, np.arange(small.size, dtype=np.uint32))
+
+
+def test_dispatch_order_planner_accepts_unsorted_lengths():
+    """The first-wave check takes the n_workers LONGEST jobs wherever they sit in lens[]: short jobs in front of
+    long ones must not make a batch look as if its first wave fitted the pool."""
+    import ctypes as C
+    from nanocall_b200 import _lib
+    lib = _lib.load()
+    workers, pool = 4, 1000
+    lens = np.array([10] * 8 + [400] * 8, np.uint32)          # ascending: the four longest need 1600 > 900 columns
+    perm = np.zeros(lens.size, np.uint32)
+    assert lib.nc_plan_dispatch_order(lens.size, lens.ctypes.data, C.c_uint64(pool), workers, perm.ctypes.data) == 1
+    assert np.array_equal(np.sort(perm), np.arange(lens.size, dtype=np.uint32))
+    assert lens[perm[0]] == 400                                # the longest job that fits starts first
