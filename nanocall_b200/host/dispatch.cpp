@@ -299,11 +299,8 @@ bool run_pipeline(const Run_Config& cfg, Read_Source& src, std::ostream* fasta, 
                         t_first_batch = Clock::now();
                     }
                     std::vector< Read* > rp;
-                    for (auto& it : batch)
-                    {
-                        p->init_read_params(it.read);
-                        rp.push_back(&it.read);
-                    }
+                    for (auto& it : batch) rp.push_back(&it.read);
+                    p->init_reads_params(rp);
                     const auto a0 = Clock::now();
                     if (cfg.opt.train) p->train_reads(rp);
                     ds.train_s += secs(a0, Clock::now());

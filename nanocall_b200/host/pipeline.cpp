@@ -180,6 +180,12 @@ void Pipeline::reserve(size_t reads, size_t events)
     // basecalling: every strand once per candidate still in the race (two at most with the builtin presets)
     const size_t vit_events = opt_.basecall ? 2 * events : 0;
     check(nc_ctx_reserve(ctx_, train_events, vit_events), "nc_ctx_reserve");
+    if (train_events)
+    {
+        pin_tr_mean_.reserve(train_events * sizeof(float));
+        pin_tr_stdv_.reserve(train_events * sizeof(float));
+        pin_tr_start_.reserve(train_events * sizeof(float));
+    }
     if (vit_events)
     {
         pin_mean_.reserve(vit_events * sizeof(float));
@@ -277,6 +283,29 @@ void Pipeline::init_read_params(Read& r) const
 
 // ---------------------------------------------------------------- training (nanocall.cpp:275-582)
 namespace {
+// fn(i) for i in [0, n) on up to n_threads threads (contiguous ranges; fn must not throw)
+template < typename Fn >
+void parallel_for(size_t n, unsigned n_threads, Fn fn)
+{
+    n_threads = (unsigned)std::min< size_t >(n_threads, (n + 63) / 64);
+    if (n_threads <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+    std::vector< std::thread > th;
+    for (unsigned t = 0; t < n_threads; ++t)
+        th.emplace_back([&, t] {
+            const size_t a = n * t / n_threads, b = n * (t + 1) / n_threads;
+            for (size_t i = a; i < b; ++i) fn(i);
+        });
+    for (auto& x : th) x.join();
+}
+} // namespace
+
+void Pipeline::init_reads_params(std::vector< Read* >& reads) const
+{
+    // (a pass over every event of every read for the initial scaling: 40 ms per 4096-read batch on one thread)
+    parallel_for(reads.size(), opt_.host_threads, [&](size_t k) { init_read_params(*reads[k]); });
+}
+
+namespace {
 struct Candidate
 {
     size_t read;
@@ -292,6 +321,7 @@ struct Candidate
     // packed training sequences of this candidate
     std::vector< uint8_t > seq_strand;
     std::vector< uint32_t > seq_len;
+    std::vector< size_t > seq_from;   // first event of the sequence in its strand
     std::vector< float > mean, stdv, start;
 };
 } // namespace
@@ -322,9 +352,7 @@ void Pipeline::train_reads(std::vector< Read* >& reads)
             {
                 c.seq_strand.push_back((uint8_t)st);
                 c.seq_len.push_back(h);
-                c.mean.insert(c.mean.end(), ev.mean.begin() + from[part], ev.mean.begin() + from[part] + h);
-                c.stdv.insert(c.stdv.end(), ev.stdv.begin() + from[part], ev.stdv.begin() + from[part] + h);
-                c.start.insert(c.start.end(), ev.start.begin() + from[part], ev.start.begin() + from[part] + h);
+                c.seq_from.push_back(from[part]);   // (the events are copied below, on the helper threads)
             }
         };
         auto make = [&](const Model_Key& key, unsigned strand) {
@@ -371,6 +399,22 @@ void Pipeline::train_reads(std::vector< Read* >& reads)
             }
         }
     }
+    parallel_for(cands.size(), opt_.host_threads, [&](size_t k) {
+        Candidate& c = cands[k];
+        const Read& rd = *reads[c.read];
+        size_t n = 0;
+        for (auto l : c.seq_len) n += l;
+        c.mean.resize(n); c.stdv.resize(n); c.start.resize(n);
+        size_t at = 0;
+        for (size_t q = 0; q < c.seq_len.size(); ++q)
+        {
+            const Strand_Events& ev = rd.events[c.seq_strand[q]];
+            std::memcpy(c.mean.data() + at, ev.mean.data() + c.seq_from[q], c.seq_len[q] * sizeof(float));
+            std::memcpy(c.stdv.data() + at, ev.stdv.data() + c.seq_from[q], c.seq_len[q] * sizeof(float));
+            std::memcpy(c.start.data() + at, ev.start.data() + c.seq_from[q], c.seq_len[q] * sizeof(float));
+            at += c.seq_len[q];
+        }
+    });
     // drop candidates whose sequences are empty (n/2 == 0 cannot happen with min_ed_events >= 2, but be safe)
     for (auto& c : cands)
         for (auto l : c.seq_len)
@@ -384,9 +428,8 @@ void Pipeline::train_reads(std::vector< Read* >& reads)
     // ---- EM rounds: every active candidate advances by one train_one_round per batch call (:367-426, :483-542)
     std::vector< size_t > act;
     std::vector< uint32_t > seq_off;
-    std::vector< uint64_t > ev_off;
+    std::vector< uint64_t > ev_off, cand_ev;
     std::vector< uint8_t > strands;
-    std::vector< float > mean, stdv, start;
     std::vector< nc_train_in > tin;
     std::vector< nc_train_out > tout;
     for (;;)
@@ -395,34 +438,45 @@ void Pipeline::train_reads(std::vector< Read* >& reads)
         for (size_t k = 0; k < cands.size(); ++k)
             if (cands[k].active) act.push_back(k);
         if (act.empty()) break;
+        // offsets first (serial, light), then the candidates' events into the packed arrays on the helper threads: the
+        // copy is the bulk of the host time between two calls, and the GPU waits for it
         seq_off.assign(1, 0);
         ev_off.assign(1, 0);
-        strands.clear(); mean.clear(); stdv.clear(); start.clear();
+        strands.clear();
         tin.resize(act.size());
         tout.resize(act.size());
+        cand_ev.resize(act.size());
         for (size_t a = 0; a < act.size(); ++a)
         {
             const Candidate& c = cands[act[a]];
+            cand_ev[a] = ev_off.back();
             for (size_t s = 0; s < c.seq_len.size(); ++s)
             {
                 strands.push_back(c.seq_strand[s]);
                 ev_off.push_back(ev_off.back() + c.seq_len[s]);
             }
             seq_off.push_back(seq_off.back() + (uint32_t)c.seq_len.size());
-            mean.insert(mean.end(), c.mean.begin(), c.mean.end());
-            stdv.insert(stdv.end(), c.stdv.begin(), c.stdv.end());
-            start.insert(start.end(), c.start.begin(), c.start.end());
             tin[a].model_id[0] = c.model_id[0];
             tin[a].model_id[1] = c.model_id[1];
             tin[a].pm = c.crt_pm;
             tin[a].st[0] = c.crt_st[0];
             tin[a].st[1] = c.crt_st[1];
         }
+        // (page-locked: the call's three uploads are plain DMA instead of staged copies)
+        float* mean = static_cast< float* >(pin_tr_mean_.reserve(ev_off.back() * sizeof(float)));
+        float* stdv = static_cast< float* >(pin_tr_stdv_.reserve(ev_off.back() * sizeof(float)));
+        float* start = static_cast< float* >(pin_tr_start_.reserve(ev_off.back() * sizeof(float)));
+        parallel_for(act.size(), opt_.host_threads, [&](size_t a) {
+            const Candidate& c = cands[act[a]];
+            std::memcpy(mean + cand_ev[a], c.mean.data(), c.mean.size() * sizeof(float));
+            std::memcpy(stdv + cand_ev[a], c.stdv.data(), c.stdv.size() * sizeof(float));
+            std::memcpy(start + cand_ev[a], c.start.data(), c.start.size() * sizeof(float));
+        });
         {
             std::lock_guard< std::mutex > gpu(gpu_mu_);
             const auto c0 = std::chrono::steady_clock::now();
             check(nc_train_round_batch(ctx_, (uint32_t)act.size(), seq_off.data(), ev_off.data(), strands.data(),
-                                       mean.data(), stdv.data(), start.data(), tin.data(), &topts, tout.data()),
+                                       mean, stdv, start, tin.data(), &topts, tout.data()),
                   "nc_train_round_batch");
             train_call_s += std::chrono::duration< double >(std::chrono::steady_clock::now() - c0).count();
             train_kernel_ms += nc_ctx_last_kernel_ms(ctx_);
@@ -529,22 +583,6 @@ void* Pipeline::Pinned::reserve(size_t bytes)
 }
 Pipeline::Pinned::~Pinned() { if (p) nc_host_free(p); }
 
-namespace {
-// fn(i) for i in [0, n) on up to n_threads threads (contiguous ranges; fn must not throw)
-template < typename Fn >
-void parallel_for(size_t n, unsigned n_threads, Fn fn)
-{
-    n_threads = (unsigned)std::min< size_t >(n_threads, (n + 63) / 64);
-    if (n_threads <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
-    std::vector< std::thread > th;
-    for (unsigned t = 0; t < n_threads; ++t)
-        th.emplace_back([&, t] {
-            const size_t a = n * t / n_threads, b = n * (t + 1) / n_threads;
-            for (size_t i = a; i < b; ++i) fn(i);
-        });
-    for (auto& x : th) x.join();
-}
-} // namespace
 
 void Pipeline::basecall_reads(std::vector< Read* >& reads)
 {

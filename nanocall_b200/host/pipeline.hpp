@@ -108,6 +108,7 @@ public:
     // that the first batch does not pay for it
     void reserve(size_t reads, size_t events);
     void init_read_params(Read& r) const;
+    void init_reads_params(std::vector< Read* >& reads) const;   // the same for a batch, on the helper threads
     void train_reads(std::vector< Read* >& reads);
     void basecall_reads(std::vector< Read* >& reads);
     static void write_fasta(std::ostream& os, const std::string& name, const std::string& seq, unsigned width);
@@ -134,6 +135,7 @@ private:
         ~Pinned();
     };
     Pinned pin_mean_, pin_stdv_, pin_start_, pin_states_, pin_moves_;
+    Pinned pin_tr_mean_, pin_tr_stdv_, pin_tr_start_;   // the packed training sequences of an EM round (train_reads)
     Options opt_;
     nc_ctx* ctx_ = nullptr;
     // train_reads and basecall_reads may run on two threads (dispatch.cpp trains batch k+1 while batch k is basecalled):
