@@ -46,6 +46,9 @@
 #include <cstring>
 #include <type_traits>
 
+#ifndef NC_VIT_OPAQUE
+#define NC_VIT_OPAQUE 1
+#endif
 #ifndef NC_EXP
 #define NC_EXP 0   // timing experiments (tools/build_variants.sh); anything but 0 is not a product build
 #endif
@@ -653,13 +656,18 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
         // shared-memory addresses of the exchange slots (buffer 0; buffer 1 is + X2_BUF / X1_BUF bytes)
         constexpr unsigned X2_BUF = X2_FLOATS * sizeof(float), X1_BUF = X1_FLOATS * sizeof(float);
         const unsigned x2_0 = smem_u32(&sm.x2[0][0]), x1_0 = smem_u32(&sm.x1[0][0]);
-        const unsigned wr_x2 = x2_0 + 4u * pos_x2(T);                       // written by the half == 0 thread
-        const unsigned wr_x1 = x1_0 + 4u * pos_x1(Ha);                      // Ha, Hb are adjacent floats
+        unsigned wr_x2 = x2_0 + 4u * pos_x2(T);                       // written by the half == 0 thread
+        unsigned wr_x1 = x1_0 + 4u * pos_x1(Ha);                      // Ha, Hb are adjacent floats
         // candidates of states k = 0..3 (b' = 2 half) and k = 4..7 (b' = 2 half + 1): one float4 each per class
         // (the float4 of b' = 2 half + 1 lies 16 bytes after the one of b' = 2 half)
-        const unsigned rd_x2 = x2_0 + 4u * pos_x2(((2u * half) << 4) | (T >> 4));
-        const unsigned rd_x1 = x1_0 + 4u * pos_x1(((2u * half) << 6) | (T >> 2));
+        unsigned rd_x2 = x2_0 + 4u * pos_x2(((2u * half) << 4) | (T >> 4));
+        unsigned rd_x1 = x1_0 + 4u * pos_x1(((2u * half) << 6) | (T >> 2));
         const unsigned ev_b = smem_u32(&sm.ev[0]);
+#if NC_VIT_OPAQUE
+        // ptxas recomputes these shared-memory addresses from threadIdx inside the column loop (LEA.HI, IMAD, IADD3 per
+        // column) unless their origin is hidden; with it hidden they stay in registers
+        asm volatile("" : "+r"(wr_x2), "+r"(wr_x1), "+r"(rd_x2), "+r"(rd_x1));
+#endif
         const unsigned lane0 = (lane == 0) ? 1u : 0u, half0 = half ^ 1u;
         float* gcol = acol + SPT * t;                                       // this thread's 8 slots of a stored column
 
