@@ -16,8 +16,8 @@ JSON line keys beyond the base contract:
                 `traffic` = DRAM bytes per launch from the committed ncu capture (the kernel streams the alpha
                 columns, 16 KiB/event, by design: DESIGN.md K1a)
   roofline_issue executed work: the kernel's warp instructions per event (ncu smsp__inst_executed on this very launch,
-                profiles/r2_ncu_viterbi_alpha_10kx10k_summary.md) x events/s against the issue peak of 148 SMs x 4
-                sub-partitions x SM clock under load; the FMA-heavy pipe, the busiest one, was 68.8 % active in that capture.
+                profiles/r2_ncu_viterbi_alpha_10kx10k_final_summary.md) x events/s against the issue peak of 148 SMs x 4
+                sub-partitions x SM clock under load; the FMA-heavy pipe, the busiest one, was 67.0 % active in that capture.
                 (The algorithmic count of SURVEY 8d, 245,600 FP32 op/event, is NOT used as a roof: sharing the class maxima
                 removes two thirds of the per-edge operations, so a fraction built on it exceeds 1.)
   roofline_rf   what binds (profiles/r1_viterbi_alpha_experiments.md): register-file operand reads,
@@ -54,10 +54,11 @@ FP32_OPS_PER_EVENT = 245600
 RF_READS_PER_EVENT = 404 * 512  # operand reads per thread and column x threads (nc_viterbi_alpha.cu header)
 # dram__bytes_read.sum + dram__bytes_write.sum per event of viterbi_alpha_kernel, from the committed capture
 # measured on the bench's own launch (10000 reads x 10000 events, one kernel): 1.6387 TB written + 47.4 GB read
-NCU_DRAM_BYTES_PER_EVENT = {"viterbi_alpha_kernel": 16862.0, "source": "profiles/r2_ncu_viterbi_alpha_10kx10k_summary.md"}
-# executed work of the same launch: smsp__inst_executed.sum = 248.68e9 warp instructions for 1e8 events
-NCU_WARP_INSTR_PER_EVENT = {"viterbi_alpha_kernel": 2486.8, "fmaheavy_pipe_pct": 68.8, "issue_active_pct": 54.8,
-                            "source": "profiles/r2_ncu_viterbi_alpha_10kx10k_summary.md"}
+NCU_DRAM_BYTES_PER_EVENT = {"viterbi_alpha_kernel": 16861.0, "source": "profiles/r2_ncu_viterbi_alpha_10kx10k_final_summary.md"}
+# executed work of the same launch: smsp__inst_executed.sum = 217.47e9 warp instructions for 1e8 events (248.68e9 before the
+# exchange-buffer addresses were kept in registers and the column loop ran eight columns per trip)
+NCU_WARP_INSTR_PER_EVENT = {"viterbi_alpha_kernel": 2174.7, "fmaheavy_pipe_pct": 67.0, "issue_active_pct": 53.6,
+                            "source": "profiles/r2_ncu_viterbi_alpha_10kx10k_final_summary.md"}
 MODEL = "r73.t.006.ont.model"
 
 

@@ -46,6 +46,9 @@
 #include <cstring>
 #include <type_traits>
 
+#ifndef NC_VIT_UNROLL
+#define NC_VIT_UNROLL 8   // columns per trip of the forward loop (2 = the bare two-column body)
+#endif
 #ifndef NC_VIT_OPAQUE
 #define NC_VIT_OPAQUE 1
 #endif
@@ -776,6 +779,19 @@ __device__ __forceinline__ void forward_cta(const VitArgs& a)
         };
         auto columns = [&](auto ga_tag) {
             unsigned i = 1;
+#if NC_VIT_UNROLL >= 4
+            // NC_VIT_UNROLL columns per trip: the register moves ptxas needs at the loop's back edge (the carried alpha and
+            // emission pairs end a trip in other registers than they entered it) are paid that much less often
+            for (; i + (NC_VIT_UNROLL - 1) < n; i += NC_VIT_UNROLL)
+            {
+#pragma unroll
+                for (unsigned k = 0; k < NC_VIT_UNROLL; k += 2)
+                {
+                    column(std::integral_constant< unsigned, 1 >{}, ga_tag, i + k);
+                    column(std::integral_constant< unsigned, 0 >{}, ga_tag, i + k + 1);
+                }
+            }
+#endif
             for (; i + 1 < n; i += 2)
             {
                 column(std::integral_constant< unsigned, 1 >{}, ga_tag, i);
