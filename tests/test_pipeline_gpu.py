@@ -195,3 +195,23 @@ def test_pipeline_parity_golden(tmp_path, models):
     assert n_same / n >= 0.999, report
     assert worst_pm < 1e-4 + 2e-6, report          # the log prints 6 significant digits
     assert n_rounds_same == n_keys and n_sel_same == n, report
+
+
+def test_overlapped_dispatch_equals_serial_dispatch(tmp_path):
+    """host/dispatch.cpp: a dispatcher's second thread basecalls batch k while batch k+1 is trained (one context, calls
+    serialised), and nc_train_round_batch keeps two waves in flight.  Several small batches through both dispatch modes:
+    FASTA, --stats and the per-read log lines must be the same, in the same (input) order for the records."""
+    def run(tag, extra):
+        out, stats = os.path.join(tmp_path, tag + ".fa"), os.path.join(tmp_path, tag + ".tsv")
+        cmd = [CLI, "--pore", "r73", "--synth", "300:7:64:2d:700:600", "--batch-reads", "64", "-o", out, "--stats", stats,
+               "--log", "info"] + extra
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        lines = sorted(l for l in p.stderr.splitlines() if l.startswith(("scaling_result", "selected_model", "best_model")))
+        return open(out).read(), open(stats).read(), lines
+
+    fa_o, st_o, log_o = run("overlap", [])
+    fa_s, st_s, log_s = run("serial", ["--no-overlap"])
+    assert fa_o.count(">") >= 500 and fa_o == fa_s
+    assert st_o == st_s
+    assert len(log_o) > 900 and log_o == log_s
