@@ -40,7 +40,11 @@
 // barrier wait of column i -- 11 % faster than splitting it around the recursion step, and faster than staggering
 // the warps of a sub-partition (NC_EXP=6) or computing it ahead of the step (NC_EXP=7); (3) no integer arithmetic
 // in the loop (IMAD shares the FMA pipe at half rate); (4) events are staged by cp.async so no registers are held
-// across columns.  Under sustained load the GPU runs into its 1000 W power cap (SM clock 1875 of 1965 MHz).
+// across columns; (5) the exchange-buffer addresses are hidden from ptxas (NC_VIT_OPAQUE: it recomputed them from threadIdx
+// in every column) and the loop runs eight columns per trip (NC_VIT_UNROLL: the register moves at the back edge are paid a
+// quarter as often): 1115 -> 992 cycles per column, 2487 -> 2175 executed warp instructions per event
+// (profiles/r2_viterbi_alpha_loop.md).  Under sustained load the GPU runs into its 1000 W power cap (SM clock 1790-1930 of
+// 1965 MHz).
 #include "nc_vit_common.cuh"
 
 #include <cstring>
