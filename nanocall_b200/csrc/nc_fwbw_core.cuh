@@ -281,15 +281,21 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
     const float* pO = A + C.offO;   // the O pair of the next one-step slot, advanced by 1280 floats per such slot
     int so = C.c;                   // the next one-step slot
     float P[2] = { NI, NI };
-    // ---- slots below the self slot: one chain per half
-    for (int s = 0; s < C.sS; ++s, pT += 320)
+    // ---- slots below the self slot: one chain per half.  The loops run from one-step slot to one-step slot (so is the
+    // next one): plain counted loops over the two-step-only slots in between, without a test per slot
+    int s = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    while (so < C.sS)
     {
-        const float xT = fadd(C.wT, *pT);
-        if (s == so)
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+        for (; s < so; ++s, pT += 320) flogsum_n< 2 >(P, fadd(C.wT, *pT), tbl);
         {
+            const float xT = fadd(C.wT, *pT);
             const float2 o = *reinterpret_cast< const float2* >(pO);
-            so += 4;
-            pO += 1280;
             const float xO0 = fadd(C.wO[0], o.x), xO1 = fadd(C.wO[1], o.y);
             const float a0 = oBef0 ? xO0 : (oEq0 ? NI : xT), b0 = oBef0 ? xT : xO0;
             const float a1 = oBef1 ? xO1 : (oEq1 ? NI : xT), b1 = oBef1 ? xT : xO1;
@@ -297,8 +303,12 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
             flogsum_n< 2 >(P, xa, tbl);
             flogsum_n< 2 >(P, xb, tbl);
         }
-        else flogsum_n< 2 >(P, xT, tbl);
+        ++s; pT += 320; so += 4; pO += 1280;
     }
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (; s < C.sS; ++s, pT += 320) flogsum_n< 2 >(P, fadd(C.wT, *pT), tbl);
     // ---- the self slot: per state
     float acc[8];
     {
@@ -355,15 +365,20 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
             flogsum_n< 8 >(acc, e2, tbl);
         }
     }
-    // ---- slots above the self slot: per state
-    for (int s = C.sS + 1; s < 16; ++s, pT += 320)
+    // ---- slots above the self slot: per state, again from one-step slot to one-step slot
+    s = C.sS + 1;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    while (so < 16)
     {
-        const float xT = fadd(C.wT, *pT);
-        if (s == so)
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+        for (; s < so; ++s, pT += 320) flogsum_n< 8 >(acc, fadd(C.wT, *pT), tbl);
         {
+            const float xT = fadd(C.wT, *pT);
             const float2 o = *reinterpret_cast< const float2* >(pO);
-            so += 4;
-            pO += 1280;
             const float xO0 = fadd(C.wO[0], o.x), xO1 = fadd(C.wO[1], o.y);
             const float a0 = oBef0 ? xO0 : (oEq0 ? NI : xT), b0 = oBef0 ? xT : xO0;
             const float a1 = oBef1 ? xO1 : (oEq1 ? NI : xT), b1 = oBef1 ? xT : xO1;
@@ -371,8 +386,12 @@ NC_HD void fwd_column(const FwdConst& C, const float* __restrict__ A, const TB& 
             flogsum_n< 8 >(acc, xa, tbl);
             flogsum_n< 8 >(acc, xb, tbl);
         }
-        else flogsum_n< 8 >(acc, xT, tbl);
+        ++s; pT += 320; so += 4; pO += 1280;
     }
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (; s < 16; ++s, pT += 320) flogsum_n< 8 >(acc, fadd(C.wT, *pT), tbl);
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
