@@ -215,3 +215,31 @@ def test_overlapped_dispatch_equals_serial_dispatch(tmp_path):
     assert fa_o.count(">") >= 500 and fa_o == fa_s
     assert st_o == st_s
     assert len(log_o) > 900 and log_o == log_s
+
+
+def test_model_files_and_model_fofn_equal_the_builtin_models(tmp_path, models):
+    """-m/--model strand:file and --model-fofn (nanocall.cpp:97-153, Pore_Model::operator>>, Pore_Model.hpp:251-287): the
+    builtin r73 tables written out as model files (k-mer, level mean, level stdv, sd mean, sd stdv; 9 significant digits
+    round-trip a float) must give the same basecalls as the builtin models, through either option."""
+    reads = _make_reads(models, 21, 10)
+    extra = ["--scaling-num-events", "80", "--scaling-max-rounds", "4"]
+    base_fa, _, _ = _run_cli(str(tmp_path), reads, extra)
+    mdir = os.path.join(str(tmp_path), "models")
+    os.makedirs(mdir)
+    specs = []
+    for name in R73:
+        t = np.asarray(models[name]["table"], np.float32).reshape(4096, 4)
+        path = os.path.join(mdir, name)
+        with open(path, "w") as f:
+            f.write("#a comment line\nkmer\tlevel_mean\tlevel_stdv\tsd_mean\tsd_stdv\n")
+            for j in range(4096):
+                kmer = "".join("ACGT"[(j >> (2 * (5 - b))) & 3] for b in range(6))
+                f.write(kmer + "\t" + "\t".join("%.9g" % v for v in t[j]) + "\n")
+        specs.append(("0" if ".t." in name else "1") + ":" + path)
+    by_m, err_m, _ = _run_cli(str(tmp_path), reads, extra + [a for s in specs for a in ("-m", s)])
+    fofn = os.path.join(mdir, "models.fofn")
+    open(fofn, "w").write("\n".join(specs) + "\n")
+    by_f, _, _ = _run_cli(str(tmp_path), reads, extra + ["--model-fofn", fofn])
+    assert len(base_fa) == 2 * len(reads)
+    assert by_m == base_fa and by_f == base_fa
+    assert err_m.count("loaded module") == 3 and specs[0][2:] in err_m
