@@ -199,7 +199,8 @@ void nc_transition_lut(float p_stay, float p_skip, float* lut64);
 uint32_t nc_min_skip(uint32_t k1, uint32_t k2);
 /* Dispatch order of the Viterbi jobs of one call (host helper, no device needed): lens[] descending, pool_columns =
  * alpha columns (16 KiB each) in the scratch pool, n_workers = forward CTAs.  perm[k] = index of the k-th job to
- * start: longest-first whenever the columns of the running jobs leave room, shorter jobs while memory is tight.
+ * start: longest-first whenever the columns of the running jobs leave room, shorter jobs while memory is tight
+ * (lens[] in any order is accepted: the first-wave check looks for the n_workers longest jobs itself).
  * Returns 1 when the order was changed, 0 when longest-first is kept (perm = identity). */
 int nc_plan_dispatch_order(uint32_t n_jobs, const uint32_t* lens, uint64_t pool_columns, uint32_t n_workers, uint32_t* perm);
 /* library version string */

@@ -5,6 +5,8 @@
 // reference does: double accumulation over events in order, 3x3 Gaussian elimination with scaled partial
 // pivoting (:339-390), var / scale_sd / var_sd (:406-426), exp of the accumulator differences and clamps
 // (:516-530).
+// A call's groups are cut into waves that fit the E|alpha|beta scratch; two waves are in flight (submit_wave /
+// collect_wave): the host builds and queues wave k+1 while wave k's kernels run, statistics come back on a fourth stream.
 #include "nc_ctx.h"
 
 #include <algorithm>
