@@ -29,16 +29,16 @@ std::string islands_str(const Islands& v)
 }
 
 // Fast5_Summary::find_islands_5_consec (:545-571): runs of >= 5 consecutive events at or above the abasic level
-Islands find_islands_5_consec(const std::vector< Ed_Event >& ed, float abasic_level)
+Islands find_islands_5_consec(const Ed_Event* ed, size_t n_ed, float abasic_level)
 {
     Islands islands;
     unsigned i = 0;
-    while (i < ed.size())
+    while (i < n_ed)
     {
         if (ed[i].mean >= abasic_level)
         {
             unsigned j = i + 1;
-            while (j < ed.size() && ed[j].mean >= abasic_level) ++j;
+            while (j < n_ed && ed[j].mean >= abasic_level) ++j;
             if (j - i >= 5) islands.push_back(std::make_pair(i, j));
             i = j + 1;
         }
@@ -48,11 +48,11 @@ Islands find_islands_5_consec(const std::vector< Ed_Event >& ed, float abasic_le
 }
 
 // Fast5_Summary::detect_strands (:653-731)
-void detect_strands(const Options& opt, const std::vector< Ed_Event >& ed, float abasic_level, const std::string& read_id,
+void detect_strands(const Options& opt, const Ed_Event* ed, size_t n_ed, float abasic_level, const std::string& read_id,
                     std::array< unsigned, 4 >& sb)
 {
     const auto& tm = opt.trim_margins;
-    Islands islands = find_islands_5_consec(ed, abasic_level);
+    Islands islands = find_islands_5_consec(ed, n_ed, abasic_level);
     for (unsigned i = 1; i < islands.size(); ++i)
     {
         if (islands[i - 1].second + std::max(tm[2], tm[3]) >= islands[i].first)
@@ -69,13 +69,13 @@ void detect_strands(const Options& opt, const std::vector< Ed_Event >& ed, float
         return;
     }
     auto dist_to_middle = [&](const std::pair< unsigned, unsigned >& p) {
-        return std::min((unsigned)std::abs((long)p.first - (long)ed.size() / 2),
-                        (unsigned)std::abs((long)p.second - (long)ed.size() / 2));
+        return std::min((unsigned)std::abs((long)p.first - (long)n_ed / 2),
+                        (unsigned)std::abs((long)p.second - (long)n_ed / 2));
     };
     auto it = islands.begin();   // alg::min_of: the first minimum
     for (auto jt = islands.begin() + 1; jt != islands.end(); ++jt)
         if (dist_to_middle(*jt) < dist_to_middle(*it)) it = jt;
-    if (dist_to_middle(*it) > ed.size() / 6)
+    if (dist_to_middle(*it) > n_ed / 6)
     {
         log_line(2, opt.log_level, "drop_read read_id=[" + read_id + "] islands=[" + islands_str(islands) + "]");
         return;
@@ -84,8 +84,8 @@ void detect_strands(const Options& opt, const std::vector< Ed_Event >& ed, float
     if (islands[0].first < tm[0] + tm[2]) sb[0] = std::max(sb[0], islands[0].second);
     sb[1] = it->first - tm[2];
     sb[2] = it->first + tm[3];
-    sb[3] = (unsigned)ed.size() - tm[1];
-    if (islands[islands.size() - 1].second > ed.size() - (tm[3] + tm[1])) sb[3] = std::min(sb[3], islands[islands.size() - 1].first);
+    sb[3] = (unsigned)n_ed - tm[1];
+    if (islands[islands.size() - 1].second > n_ed - (tm[3] + tm[1])) sb[3] = std::min(sb[3], islands[islands.size() - 1].first);
 }
 
 std::string base_name_of(const std::string& file_name)
@@ -100,12 +100,18 @@ std::string base_name_of(const std::string& file_name)
 
 bool summarize_raw_read(const Options& opt, Raw_Read&& raw, Read& r, std::string& why)
 {
+    return summarize_events(opt, raw.file_name, raw.read_id, raw.sampling_rate, raw.ed.data(), raw.ed.size(), r, why);
+}
+
+// (the events are only read: the synthetic source summarises its pool reads in place, without a copy per replay)
+bool summarize_events(const Options& opt, const std::string& fn, const std::string& raw_read_id, double raw_sampling_rate,
+                      const Ed_Event* ed, size_t n_raw, Read& r, std::string& why)
+{
     r = Read();
-    r.base_file_name = base_name_of(raw.file_name);
+    r.base_file_name = base_name_of(fn);
     r.read_id = r.base_file_name;
-    const std::string& fn = raw.file_name;
-    if (!(raw.sampling_rate > 0)) { why = fn + ": missing sampling rate"; return false; }
-    r.sampling_rate = (float)raw.sampling_rate;
+    if (!(raw_sampling_rate > 0)) { why = fn + ": missing sampling rate"; return false; }
+    r.sampling_rate = (float)raw_sampling_rate;
     if (r.sampling_rate < 1000.0 || r.sampling_rate > 10000.0)
     {
         std::ostringstream os;
@@ -113,18 +119,17 @@ bool summarize_raw_read(const Options& opt, Raw_Read&& raw, Read& r, std::string
         why = os.str();
         return false;
     }
-    if (!raw.read_id.empty()) r.read_id = raw.read_id;
-    std::vector< Ed_Event >& ed = raw.ed;
+    if (!raw_read_id.empty()) r.read_id = raw_read_id;
     // load_ed_events (:505-525)
-    if (ed.size() > opt.max_ed_events)
+    if (n_raw > opt.max_ed_events)
     {
         std::ostringstream os;
-        os << fn << ": using only " << opt.max_ed_events << " of " << ed.size() << " events";
+        os << fn << ": using only " << opt.max_ed_events << " of " << n_raw << " events";
         log_line(2, opt.log_level, os.str());
         r.num_ed_events = opt.max_ed_events;
     }
-    else r.num_ed_events = (unsigned)ed.size();
-    ed.resize(r.num_ed_events);
+    else r.num_ed_events = (unsigned)n_raw;
+    const size_t n_ed = r.num_ed_events;
     const auto& tm = opt.trim_margins;
     if (r.num_ed_events < tm[0] + tm[1] + opt.min_ed_events)
     {
@@ -137,8 +142,8 @@ bool summarize_raw_read(const Options& opt, Raw_Read&& raw, Read& r, std::string
     // detect_abasic_level (:527-543): the level below the top percent of the event means, plus the preset's offset.
     // (the reference sorts; the order statistic is the same)
     {
-        std::vector< float > s(ed.size());
-        for (size_t i = 0; i < ed.size(); ++i) s[i] = (float)ed[i].mean;
+        std::vector< float > s(n_ed);
+        for (size_t i = 0; i < n_ed; ++i) s[i] = (float)ed[i].mean;
         size_t k = (size_t)((double)s.size() * (1.0 - opt.abasic_level_top_percent / 100.0));
         if (k >= s.size()) k = s.size() - 1;   // (top percent 0 indexes past the end in the reference)
         std::nth_element(s.begin(), s.begin() + k, s.end());
@@ -153,7 +158,7 @@ bool summarize_raw_read(const Options& opt, Raw_Read&& raw, Read& r, std::string
         return false;
     }
     r.strand_bounds = { { tm[0], r.num_ed_events - tm[1], 0u, 0u } };
-    if (!opt.template_only) detect_strands(opt, ed, r.abasic_level, r.read_id, r.strand_bounds);
+    if (!opt.template_only) detect_strands(opt, ed, n_ed, r.abasic_level, r.read_id, r.strand_bounds);
     const auto& sb = r.strand_bounds;
     if (sb[1] <= sb[0])
     {
@@ -412,13 +417,11 @@ public:
         const size_t k = counter_++;
         if (k >= n_reads_) return false;
         index = k;
-        Raw_Read raw = pool_[k % pool_.size()];
+        const Raw_Read& raw = pool_[k % pool_.size()];
         char id[32];
         std::snprintf(id, sizeof id, "synth%08zu", k);
-        raw.read_id = id;
-        raw.file_name = "synth.fast5";
         std::string why;
-        const bool ok = summarize_raw_read(opt_, std::move(raw), r, why);
+        const bool ok = summarize_events(opt_, "synth.fast5", id, raw.sampling_rate, raw.ed.data(), raw.ed.size(), r, why);
         if (!ok && !why.empty()) log_line(2, opt_.log_level, why);
         return true;
     }

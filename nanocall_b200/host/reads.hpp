@@ -40,6 +40,8 @@ struct Raw_Read
 // scale_strands_together).  Returns false when the reference would leave num_ed_events == 0 (the read is skipped by
 // training and basecalling but still gets a --stats row); `why` then holds the reference's log message.
 bool summarize_raw_read(const Options& opt, Raw_Read&& raw, Read& r, std::string& why);
+bool summarize_events(const Options& opt, const std::string& file_name, const std::string& read_id, double sampling_rate,
+                      const Ed_Event* ed, size_t n_raw, Read& r, std::string& why);
 
 // one record after the other; the callback returns false to stop
 bool read_ncrw_file(const std::string& path, std::vector< Raw_Read >& out, std::string& err);
