@@ -143,11 +143,43 @@ bool summarize_events(const Options& opt, const std::string& fn, const std::stri
     // (the reference sorts; the order statistic is the same)
     {
         std::vector< float > s(n_ed);
-        for (size_t i = 0; i < n_ed; ++i) s[i] = (float)ed[i].mean;
+        float lo = std::numeric_limits< float >::infinity(), hi = -lo;
+        for (size_t i = 0; i < n_ed; ++i)
+        {
+            s[i] = (float)ed[i].mean;
+            lo = std::min(lo, s[i]);
+            hi = std::max(hi, s[i]);
+        }
         size_t k = (size_t)((double)s.size() * (1.0 - opt.abasic_level_top_percent / 100.0));
         if (k >= s.size()) k = s.size() - 1;   // (top percent 0 indexes past the end in the reference)
-        std::nth_element(s.begin(), s.begin() + k, s.end());
-        r.abasic_level = (float)(s[k] + opt.abasic_level_top_offset);
+        // The k-th smallest mean, exactly, in two light passes instead of a selection over the whole read: a histogram over
+        // [lo, hi] finds the bin that holds it, the selection then runs inside that bin (a hundredth of the events).  A
+        // value's bin is a monotone function of the value, so order statistics carry over; NaN or a flat read take the
+        // plain selection.
+        float kth;
+        constexpr int NB = 1024;
+        if (hi > lo && n_ed >= 4 * NB)
+        {
+            const float scale = (float)(NB - 1) / (hi - lo);
+            auto bin = [&](float v) { int b = (int)((v - lo) * scale); return b < 0 ? 0 : (b >= NB ? NB - 1 : b); };
+            unsigned cnt[NB] = { 0 };
+            for (size_t i = 0; i < n_ed; ++i) ++cnt[bin(s[i])];
+            size_t below = 0;
+            int b = 0;
+            while (below + cnt[b] <= k) below += cnt[b++];
+            std::vector< float > in;
+            in.reserve(cnt[b]);
+            for (size_t i = 0; i < n_ed; ++i)
+                if (bin(s[i]) == b) in.push_back(s[i]);
+            std::nth_element(in.begin(), in.begin() + (k - below), in.end());
+            kth = in[k - below];
+        }
+        else
+        {
+            std::nth_element(s.begin(), s.begin() + k, s.end());
+            kth = s[k];
+        }
+        r.abasic_level = (float)(kth + opt.abasic_level_top_offset);
     }
     if (r.abasic_level <= 1.0)
     {
@@ -174,18 +206,19 @@ bool summarize_events(const Options& opt, const std::string& fn, const std::stri
         Strand_Events& ev = r.events[st];
         const unsigned b0 = sb[2 * st], b1 = sb[2 * st + 1];
         if (b1 <= b0) continue;
-        ev.mean.reserve(b1 - b0); ev.stdv.reserve(b1 - b0); ev.start.reserve(b1 - b0); ev.length.reserve(b1 - b0);
+        ev.mean.resize(b1 - b0); ev.stdv.resize(b1 - b0); ev.start.resize(b1 - b0); ev.length.resize(b1 - b0);
         const long long t0 = ed[sb[r.scale_strands_together ? 0 : 2 * st]].start;
+        size_t w = 0;   // (written unconditionally, kept by advancing w: no push_back per field and event)
         for (unsigned j = b0; j < b1; ++j)
         {
             const Ed_Event& e = ed[j];
-            if (e.mean >= r.abasic_level) continue;
-            if (e.stdv > 4.0) continue;
-            ev.mean.push_back((float)e.mean);
-            ev.stdv.push_back((float)e.stdv);
-            ev.start.push_back((float)(e.start - t0) / r.sampling_rate);
-            ev.length.push_back((float)e.length / r.sampling_rate);
+            ev.mean[w] = (float)e.mean;
+            ev.stdv[w] = (float)e.stdv;
+            ev.start[w] = (float)(e.start - t0) / r.sampling_rate;
+            ev.length[w] = (float)e.length / r.sampling_rate;
+            w += (e.mean >= r.abasic_level || e.stdv > 4.0) ? 0 : 1;
         }
+        ev.mean.resize(w); ev.stdv.resize(w); ev.start.resize(w); ev.length.resize(w);
     }
     return true;
 }
